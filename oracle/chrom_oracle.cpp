@@ -1,0 +1,521 @@
+// =====================================================================================
+// chrom_oracle.cpp — CPU ORACLE.  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// A plain C++17 restatement of the arithmetic of chrom-rs's method-of-lines hot path,
+// operation by operation, in the reference's own evaluation order (IEEE f64, no FMA
+// contraction: build with -ffp-contract=off, never -ffast-math).  Only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+// this library, and only as the checker or the reported CPU baseline.  The product
+// (libchrom_cuda.so) never links, loads or calls anything in oracle/.
+//
+// Why a restatement: the reference is Rust; neither this container nor the GPU box has
+// cargo/rustc, there is no network and no vendored crates, so /root/reference cannot be
+// compiled or run.  kind = "port".
+//
+// PARITY PINNING.  The reference holds NO bit-level golden vectors for this path.  The
+// oracle is pinned against every known-answer test the reference does hold (tests/
+// test_oracle_known_answers.py, values transcribed into tests/golden/
+// reference_known_answers.json with file:line): injection semantics, Jacobian values,
+// derived quantities, A*inv(A)=I (n=2), validation-suite retention times / sigma / mass
+// recovery / Rsf, integrator order on mock ODEs.  For the n>=3 inverse paths (nalgebra
+// closed forms n=3,4 and LU n>=5) the reference has no value tests: bit-level parity is
+// UNPINNED there; those paths are cross-checked against numpy.linalg and Sherman-Morrison.
+//
+// What each function follows (paths relative to /root/reference):
+//   injection_evaluate   src/models/injection.rs:410-446
+//   single_rhs           src/models/langmuir_single.rs:391-396, 409-412, 456-511
+//   multi_jacobian       src/models/langmuir_multi.rs:627-668
+//   try_inverse          nalgebra 0.34.x (Cargo.toml:48, not vendored) src/linalg/inverse.rs
+//                        + src/linalg/lu.rs::try_invert_to + solve.rs, restated from the
+//                        published algorithm; call site langmuir_multi.rs:674-686
+//   gemv                 nalgebra blas gemv (column-by-column axcpy); call site :838
+//   multi_rhs            src/models/langmuir_multi.rs:717-899 (compute_row 770-840)
+//   rk4 / euler loops    src/solver/methods/rk4.rs:238-332, euler.rs:199-269
+//   state algebra        src/physics/traits.rs:454-491, src/physics/data.rs:1055-1108
+//   validate_state       src/solver/mod.rs:514-553
+// =====================================================================================
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <utility>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+extern "C" {
+
+// kind: 0 None, 1 Dirac(p0=time,p1=amount), 2 Gaussian(p0=center,p1=width,p2=peak),
+//       3 Rectangle(p0=start,p1=end,p2=concentration)
+struct oracle_injection {
+  int32_t kind;
+  int32_t _pad;
+  double p0, p1, p2;
+};
+
+struct oracle_single_model {
+  double lambda, langmuir_k, port_number, fe, ue, dz;
+  oracle_injection inj;
+};
+
+struct oracle_species {
+  double lambda, langmuir_k;
+  uint32_t port_number;
+  uint32_t _pad;
+  oracle_injection inj;
+};
+
+struct oracle_multi_model {
+  double fe, ue, dz, stationary_fraction;
+  uint32_t n_species;
+  uint32_t _pad;
+  const oracle_species* species;
+};
+
+}  // extern "C"
+
+namespace {
+
+// src/models/injection.rs:410-446
+inline double injection_evaluate(const oracle_injection& inj, double t) {
+  switch (inj.kind) {
+    case 1:  // Dirac: exact equality on the freshly computed stage time
+      return (t == inj.p0) ? inj.p1 : 0.0;
+    case 2: {  // Gaussian: distance=(t-center)/width; peak*exp(-distance*distance/2.0)
+      double distance = (t - inj.p0) / inj.p1;
+      return inj.p2 * std::exp(((-distance) * distance) / 2.0);
+    }
+    case 3:  // Rectangle: half-open [start,end)
+      return (t >= inj.p0 && t < inj.p1) ? inj.p2 : 0.0;
+    default:
+      return 0.0;
+  }
+}
+
+// src/models/langmuir_single.rs:456-511 (derivative_isotherm 391-396, propagation_factor 409-412)
+void single_rhs(const oracle_single_model& m, uint32_t nz, const double* c, double t, double* dc_dt) {
+  const double c_inlet = injection_evaluate(m.inj, t);
+  for (uint32_t n = 0; n < nz; ++n) {
+    const double c_n = c[n];
+    const double n_bar = m.fe / (1.0 + m.fe) * m.port_number;
+    const double denom = 1.0 + m.langmuir_k * c_n;
+    const double deriv = m.lambda + (n_bar * m.langmuir_k) / (denom * denom);
+    const double sigma = 1.0 / (1.0 + m.fe * deriv);
+    const double dc_dz = (n > 0) ? (c_n - c[n - 1]) / m.dz : (c_n - c_inlet) / m.dz;
+    dc_dt[n] = ((-sigma) * m.ue) * dc_dz;
+  }
+}
+
+// src/models/langmuir_multi.rs:627-668 ; jac is n x n column-major (jac[i + j*n] = M_ij)
+void multi_jacobian(const oracle_multi_model& m, const double* c, double* jac) {
+  const uint32_t n = m.n_species;
+  double sum_kc = 0.0;
+  for (uint32_t k = 0; k < n; ++k) sum_kc = sum_kc + m.species[k].langmuir_k * c[k];
+  const double denom = 1.0 + sum_kc;
+  const double denom_exp2 = denom * denom;
+  for (uint32_t i = 0; i < n; ++i) {
+    const oracle_species& sp_i = m.species[i];
+    const double n_bar_i = m.stationary_fraction * (double)sp_i.port_number;
+    for (uint32_t j = 0; j < n; ++j) {
+      if (i == j) {
+        const double num = n_bar_i * sp_i.langmuir_k * (denom - sp_i.langmuir_k * c[i]);
+        jac[i + j * n] = sp_i.lambda + num / denom_exp2;
+      } else {
+        const double num = (-n_bar_i) * sp_i.langmuir_k * m.species[j].langmuir_k * c[i];
+        jac[i + j * n] = num / denom_exp2;
+      }
+    }
+  }
+}
+
+// ---- nalgebra 0.34 `try_inverse` (src/linalg/inverse.rs), column-major, in place ------------
+// 4x4: the MESA-derived unrolled cofactor expansion nalgebra uses (do_inverse4).
+bool inverse4(const double* m, double* out) {
+  const double c00 = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] +
+                     m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+  const double c01 = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] -
+                     m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+  const double c02 = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] +
+                     m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+  const double c03 = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] -
+                     m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+  const double det = m[0] * c00 + m[1] * c01 + m[2] * c02 + m[3] * c03;
+  if (det == 0.0) return false;
+  double inv[16];
+  inv[0] = c00;
+  inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] -
+           m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+  inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] +
+           m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+  inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] -
+           m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+  inv[4] = c01;
+  inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] +
+           m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+  inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] -
+           m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+  inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] +
+           m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+  inv[8] = c02;
+  inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] -
+           m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+  inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] +
+            m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+  inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] -
+            m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+  inv[12] = c03;
+  inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] +
+            m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+  inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] -
+            m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+  inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] +
+            m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+  const double inv_det = 1.0 / det;
+  for (int k = 0; k < 16; ++k) out[k] = inv[k] * inv_det;
+  return true;
+}
+
+// n>=5: nalgebra lu::try_invert_to — partial-pivot Gauss steps on a copy, applied to the
+// row-permuted identity through a unit-lower then an upper triangular solve (solve.rs).
+bool lu_try_invert_to(uint32_t n, double* a /* destroyed */, double* out) {
+  auto A = [&](uint32_t i, uint32_t j) -> double& { return a[i + (size_t)j * n]; };
+  auto O = [&](uint32_t i, uint32_t j) -> double& { return out[i + (size_t)j * n]; };
+  for (uint32_t j = 0; j < n; ++j)
+    for (uint32_t i = 0; i < n; ++i) O(i, j) = (i == j) ? 1.0 : 0.0;
+
+  for (uint32_t i = 0; i < n; ++i) {
+    // icamax over rows i.. of column i (first maximum wins: strict >)
+    uint32_t piv = i;
+    double the_max = std::fabs(A(i, i));
+    for (uint32_t r = i + 1; r < n; ++r) {
+      const double v = std::fabs(A(r, i));
+      if (v > the_max) {
+        the_max = v;
+        piv = r;
+      }
+    }
+    const double diag = A(piv, i);
+    if (diag == 0.0) return false;
+    if (piv != i) {
+      for (uint32_t j = 0; j < n; ++j) std::swap(O(i, j), O(piv, j));
+      for (uint32_t j = 0; j < i; ++j) std::swap(A(i, j), A(piv, j));
+      std::swap(A(i, i), A(piv, i));  // gauss_step_swap: coeffs.swap((0,0),(piv,0))
+    }
+    const double inv_diag = 1.0 / diag;
+    for (uint32_t r = i + 1; r < n; ++r) A(r, i) = A(r, i) * inv_diag;
+    for (uint32_t k = i + 1; k < n; ++k) {
+      if (piv != i) std::swap(A(i, k), A(piv, k));
+      const double neg_pivot = -A(i, k);
+      for (uint32_t r = i + 1; r < n; ++r) A(r, k) = neg_pivot * A(r, i) + A(r, k);  // axpy
+    }
+  }
+  // solve_lower_triangular_with_diag_mut(out, 1.0)
+  for (uint32_t c = 0; c < n; ++c) {
+    for (uint32_t i = 0; i + 1 < n; ++i) {
+      const double coeff = O(i, c) / 1.0;
+      for (uint32_t r = i + 1; r < n; ++r) O(r, c) = (-coeff) * A(r, i) + O(r, c);
+    }
+  }
+  // solve_upper_triangular_mut(out)
+  for (uint32_t c = 0; c < n; ++c) {
+    for (uint32_t ii = n; ii-- > 0;) {
+      const double diag = A(ii, ii);
+      if (diag == 0.0) return false;
+      const double coeff = O(ii, c) / diag;
+      O(ii, c) = coeff;
+      for (uint32_t r = 0; r < ii; ++r) O(r, c) = (-coeff) * A(r, ii) + O(r, c);
+    }
+  }
+  return true;
+}
+
+// Dispatch on runtime dimension exactly like nalgebra's try_inverse_mut.
+bool try_inverse(uint32_t n, const double* a, double* out) {
+  switch (n) {
+    case 0:
+      return true;
+    case 1: {
+      const double det = a[0];
+      if (det == 0.0) return false;
+      out[0] = 1.0 / det;
+      return true;
+    }
+    case 2: {
+      const double m11 = a[0], m21 = a[1], m12 = a[2], m22 = a[3];
+      const double det = m11 * m22 - m21 * m12;
+      if (det == 0.0) return false;
+      out[0] = m22 / det;
+      out[2] = (-m12) / det;
+      out[1] = (-m21) / det;
+      out[3] = m11 / det;
+      return true;
+    }
+    case 3: {
+      const double m11 = a[0], m21 = a[1], m31 = a[2];
+      const double m12 = a[3], m22 = a[4], m32 = a[5];
+      const double m13 = a[6], m23 = a[7], m33 = a[8];
+      const double minor_m12_m23 = m22 * m33 - m32 * m23;
+      const double minor_m11_m23 = m21 * m33 - m31 * m23;
+      const double minor_m11_m22 = m21 * m32 - m31 * m22;
+      const double det = m11 * minor_m12_m23 - m12 * minor_m11_m23 + m13 * minor_m11_m22;
+      if (det == 0.0) return false;
+      out[0] = minor_m12_m23 / det;                  // (0,0)
+      out[3] = (m13 * m32 - m33 * m12) / det;        // (0,1)
+      out[6] = (m12 * m23 - m22 * m13) / det;        // (0,2)
+      out[1] = (-minor_m11_m23) / det;               // (1,0)
+      out[4] = (m11 * m33 - m31 * m13) / det;        // (1,1)
+      out[7] = (m13 * m21 - m23 * m11) / det;        // (1,2)
+      out[2] = minor_m11_m22 / det;                  // (2,0)
+      out[5] = (m12 * m31 - m32 * m11) / det;        // (2,1)
+      out[8] = (m11 * m22 - m21 * m12) / det;        // (2,2)
+      return true;
+    }
+    case 4:
+      return inverse4(a, out);
+    default: {
+      std::vector<double> copy(a, a + (size_t)n * n);
+      return lu_try_invert_to(n, copy.data(), out);
+    }
+  }
+}
+
+// nalgebra gemv as used by `DMatrix * DVector`: y = A[:,0]*x[0]; y += A[:,j]*x[j], j ascending
+void gemv(uint32_t n, const double* a, const double* x, double* y) {
+  for (uint32_t i = 0; i < n; ++i) y[i] = a[i] * x[0];
+  for (uint32_t j = 1; j < n; ++j)
+    for (uint32_t i = 0; i < n; ++i) y[i] = a[i + (size_t)j * n] * x[j] + y[i];
+}
+
+struct multi_scratch {
+  std::vector<double> c_at_i, jac, mat, inv, grad, dv;
+  explicit multi_scratch(uint32_t n)
+      : c_at_i(n), jac((size_t)n * n), mat((size_t)n * n), inv((size_t)n * n), grad(n), dv(n) {}
+};
+
+// compute_row — src/models/langmuir_multi.rs:770-840.  c/dc_dt are nz x n column-major.
+void multi_row(const oracle_multi_model& m, uint32_t nz, const double* c, const double* inlet,
+               uint32_t i, double* dc_dt, multi_scratch& s, uint64_t* n_singular) {
+  const uint32_t n = m.n_species;
+  for (uint32_t k = 0; k < n; ++k) s.c_at_i[k] = c[i + (size_t)k * nz];
+  multi_jacobian(m, s.c_at_i.data(), s.jac.data());
+  for (uint32_t j = 0; j < n; ++j)
+    for (uint32_t r = 0; r < n; ++r)
+      s.mat[r + (size_t)j * n] = ((r == j) ? 1.0 : 0.0) + m.fe * s.jac[r + (size_t)j * n];
+  if (!try_inverse(n, s.mat.data(), s.inv.data())) {  // identity fallback (:790-796)
+    for (uint32_t j = 0; j < n; ++j)
+      for (uint32_t r = 0; r < n; ++r) s.inv[r + (size_t)j * n] = (r == j) ? 1.0 : 0.0;
+    if (n_singular) {
+#ifdef _OPENMP
+#pragma omp atomic
+#endif
+      ++*n_singular;
+    }
+  }
+  for (uint32_t k = 0; k < n; ++k) {
+    const double c_cur = c[i + (size_t)k * nz];
+    s.grad[k] = (i > 0) ? (c_cur - c[(i - 1) + (size_t)k * nz]) / m.dz : (c_cur - inlet[k]) / m.dz;
+  }
+  gemv(n, s.inv.data(), s.grad.data(), s.dv.data());
+  for (uint32_t k = 0; k < n; ++k) dc_dt[i + (size_t)k * nz] = (-m.ue) * s.dv[k];
+}
+
+// cells_parallel != 0 mirrors the reference's rayon fork-join over cells, taken when
+// nz*n > parallel_threshold() = 999 (langmuir_multi.rs:855-874, solver/mod.rs:385).
+void multi_rhs(const oracle_multi_model& m, uint32_t nz, const double* c, double t, double* dc_dt,
+               int cells_parallel, uint64_t* n_singular) {
+  const uint32_t n = m.n_species;
+  std::vector<double> inlet(n);
+  for (uint32_t k = 0; k < n; ++k) inlet[k] = injection_evaluate(m.species[k].inj, t);
+  if (cells_parallel && (size_t)nz * n > 999) {
+#ifdef _OPENMP
+#pragma omp parallel
+#endif
+    {
+      multi_scratch s(n);
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+      for (int64_t i = 0; i < (int64_t)nz; ++i)
+        multi_row(m, nz, c, inlet.data(), (uint32_t)i, dc_dt, s, n_singular);
+    }
+  } else {
+    multi_scratch s(n);
+    for (uint32_t i = 0; i < nz; ++i) multi_row(m, nz, c, inlet.data(), i, dc_dt, s, n_singular);
+  }
+}
+
+// validate_state — src/solver/mod.rs:514-553: NaN anywhere wins over Inf.
+// returns 0 ok, +1 NaN, -1 Inf
+int validate_state(const double* y, size_t len) {
+  bool has_nan = false, has_inf = false;
+  for (size_t i = 0; i < len; ++i) {
+    has_nan |= std::isnan(y[i]);
+    has_inf |= std::isinf(y[i]);
+  }
+  return has_nan ? 1 : (has_inf ? -1 : 0);
+}
+
+// Generic time loop over a flat state of `len` doubles.  method: 0 Euler, 1 RK4.
+// rk4.rs:238-332 / euler.rs:199-269.  trajectory: [(steps+1)][len] or NULL.
+// outlet: [n_out_series][steps+1] with series s taken from state[outlet_idx[s]], or NULL.
+template <class Rhs>
+int64_t integrate(Rhs&& rhs, int method, double total_time, uint64_t steps, size_t len, const double* y0,
+                  double* trajectory, double* outlet, const size_t* outlet_idx, size_t n_series,
+                  double* final_state) {
+  const double dt = total_time / (double)steps;
+  std::vector<double> y(len, 0.0), k1(len), k2(len), k3(len), k4(len), tmp(len);
+  if (y0) std::memcpy(y.data(), y0, len * sizeof(double));
+  auto record = [&](uint64_t slot) {
+    if (trajectory) std::memcpy(trajectory + slot * len, y.data(), len * sizeof(double));
+    if (outlet)
+      for (size_t s = 0; s < n_series; ++s) outlet[s * (steps + 1) + slot] = y[outlet_idx[s]];
+  };
+  record(0);
+  int64_t status = 0;
+  for (uint64_t step = 0; step < steps; ++step) {
+    const double t = (double)step * dt;
+    if (method == 1) {
+      rhs(y.data(), t, k1.data());
+      const double h2 = dt / 2.0;
+      for (size_t i = 0; i < len; ++i) tmp[i] = y[i] + k1[i] * h2;
+      rhs(tmp.data(), t + dt / 2.0, k2.data());
+      for (size_t i = 0; i < len; ++i) tmp[i] = y[i] + k2[i] * h2;
+      rhs(tmp.data(), t + dt / 2.0, k3.data());
+      for (size_t i = 0; i < len; ++i) tmp[i] = y[i] + k3[i] * dt;
+      rhs(tmp.data(), t + dt, k4.data());
+      const double h6 = dt / 6.0;
+      for (size_t i = 0; i < len; ++i) {
+        const double weighted = ((k1[i] + k2[i] * 2.0) + k3[i] * 2.0) + k4[i];
+        y[i] = y[i] + weighted * h6;
+      }
+    } else {
+      rhs(y.data(), t, k1.data());
+      for (size_t i = 0; i < len; ++i) y[i] = y[i] + k1[i] * dt;
+    }
+    record(step + 1);
+    const int v = validate_state(y.data(), len);
+    if (v != 0) {
+      status = (v > 0) ? (int64_t)(step + 1) : -(int64_t)(step + 1);
+      break;
+    }
+  }
+  if (final_state) std::memcpy(final_state, y.data(), len * sizeof(double));
+  return status;
+}
+
+}  // namespace
+
+extern "C" {
+
+double oracle_injection_evaluate(const oracle_injection* inj, double t) { return injection_evaluate(*inj, t); }
+
+void oracle_single_rhs(const oracle_single_model* m, uint32_t nz, const double* c, double t, double* dc_dt) {
+  single_rhs(*m, nz, c, t, dc_dt);
+}
+
+void oracle_multi_jacobian(const oracle_multi_model* m, const double* c, double* jac) {
+  multi_jacobian(*m, c, jac);
+}
+
+// column-major n x n; returns 1 when invertible (nalgebra Some), 0 when None
+int32_t oracle_try_inverse(uint32_t n, const double* a, double* out) { return try_inverse(n, a, out) ? 1 : 0; }
+
+void oracle_gemv(uint32_t n, const double* a, const double* x, double* y) { gemv(n, a, x, y); }
+
+void oracle_multi_rhs(const oracle_multi_model* m, uint32_t nz, const double* c, double t, double* dc_dt,
+                      int32_t cells_parallel) {
+  multi_rhs(*m, nz, c, t, dc_dt, cells_parallel, nullptr);
+}
+
+// Generic integrator on a mock ODE dy/dt = a*y + b (ExponentialDecay / ConstantGrowth mock
+// models of rk4.rs:361-1103, euler.rs:299-977) — exercises the time loop alone.
+int64_t oracle_solve_linear_ode(int32_t method, double a, double b, double total_time, uint64_t steps,
+                                uint32_t len, const double* y0, double* trajectory, double* final_state) {
+  auto rhs = [&](const double* y, double, double* out) {
+    for (uint32_t i = 0; i < len; ++i) out[i] = a * y[i] + b;
+  };
+  return integrate(rhs, method, total_time, steps, len, y0, trajectory, nullptr, nullptr, 0, final_state);
+}
+
+// One LangmuirSingle column.  outlet: [steps+1] (last cell) or NULL; trajectory [(steps+1)][nz] or NULL.
+// returns status: 0 ok, +s NaN first seen after step s, -s Inf (no NaN) after step s.
+int64_t oracle_solve_single(const oracle_single_model* m, int32_t method, double total_time, uint64_t steps,
+                            uint32_t nz, const double* y0, double* trajectory, double* outlet,
+                            double* final_state) {
+  auto rhs = [&](const double* y, double t, double* out) { single_rhs(*m, nz, y, t, out); };
+  const size_t idx = nz - 1;
+  return integrate(rhs, method, total_time, steps, nz, y0, trajectory, outlet, &idx, 1, final_state);
+}
+
+// One LangmuirMulti column.  State is nz x n column-major ([species][nz]).
+// outlet: [n][steps+1]; trajectory [(steps+1)][n][nz].
+int64_t oracle_solve_multi(const oracle_multi_model* m, int32_t method, double total_time, uint64_t steps,
+                           uint32_t nz, const double* y0, double* trajectory, double* outlet,
+                           double* final_state, int32_t cells_parallel, uint64_t* n_singular) {
+  const uint32_t n = m->n_species;
+  if (n_singular) *n_singular = 0;
+  auto rhs = [&](const double* y, double t, double* out) {
+    multi_rhs(*m, nz, y, t, out, cells_parallel, n_singular);
+  };
+  std::vector<size_t> idx(n);
+  for (uint32_t k = 0; k < n; ++k) idx[k] = (size_t)k * nz + (nz - 1);
+  return integrate(rhs, method, total_time, steps, (size_t)nz * n, y0, trajectory, outlet, idx.data(), n,
+                   final_state);
+}
+
+// Batch drivers for the CPU baseline: one column per thread, OpenMP over columns.
+// outlet [n_cols][steps+1] or NULL, final_state [n_cols][nz] or NULL, status [n_cols].
+void oracle_solve_single_batch(const oracle_single_model* models, uint64_t n_cols, int32_t method,
+                               double total_time, uint64_t steps, uint32_t nz, const double* y0,
+                               double* outlet, double* final_state, int64_t* status, int32_t n_threads) {
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+  for (int64_t c = 0; c < (int64_t)n_cols; ++c) {
+    status[c] = oracle_solve_single(&models[c], method, total_time, steps, nz, y0 ? y0 + (size_t)c * nz : nullptr,
+                                    nullptr, outlet ? outlet + (size_t)c * (steps + 1) : nullptr,
+                                    final_state ? final_state + (size_t)c * nz : nullptr);
+  }
+}
+
+// models[c].species must point at that column's species array.
+// cells_parallel: 0 = one column per thread; 1 = columns sequential, cells across threads
+// (the reference's rayon path).
+void oracle_solve_multi_batch(const oracle_multi_model* models, uint64_t n_cols, int32_t method,
+                              double total_time, uint64_t steps, uint32_t nz, const double* y0, double* outlet,
+                              double* final_state, int64_t* status, int32_t n_threads, int32_t cells_parallel) {
+#ifdef _OPENMP
+  if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+  if (cells_parallel) {
+    for (uint64_t c = 0; c < n_cols; ++c) {
+      const uint32_t n = models[c].n_species;
+      status[c] = oracle_solve_multi(&models[c], method, total_time, steps, nz,
+                                     y0 ? y0 + (size_t)c * nz * n : nullptr, nullptr,
+                                     outlet ? outlet + (size_t)c * n * (steps + 1) : nullptr,
+                                     final_state ? final_state + (size_t)c * nz * n : nullptr, 1, nullptr);
+    }
+    return;
+  }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+  for (int64_t c = 0; c < (int64_t)n_cols; ++c) {
+    const uint32_t n = models[c].n_species;
+    status[c] = oracle_solve_multi(&models[c], method, total_time, steps, nz,
+                                   y0 ? y0 + (size_t)c * nz * n : nullptr, nullptr,
+                                   outlet ? outlet + (size_t)c * n * (steps + 1) : nullptr,
+                                   final_state ? final_state + (size_t)c * nz * n : nullptr, 0, nullptr);
+  }
+}
+
+int32_t oracle_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+}  // extern "C"
