@@ -1,0 +1,662 @@
+// api.cu — the C ABI of libchrom_cuda.so (include/chrom_cuda.h): contexts, plans, host-side
+// helpers that restate the reference's boundary semantics (config validation, stage-time
+// injection tables, time points, validate_state messages) and the batch -> device sharding.
+//
+// Sharding: columns are independent, so a batch is cut into contiguous column
+// ranges, one per device of the context; each device has its own stream; there is no collective.
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace chrom;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DeviceState {
+  int id = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  void* flush_buf = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // h2d0 h2d1 k0 k1 d2h0 d2h1
+};
+
+std::string format(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  return buf;
+}
+
+}  // namespace
+
+struct chrom_cuda_ctx {
+  std::vector<DeviceState> devs;
+  mutable std::string err;
+  chrom_cuda_timing timing{};
+};
+
+namespace {
+
+int32_t fail(const chrom_cuda_ctx* ctx, int32_t code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                       \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return fail(ctx, CHROM_ERR_CUDA, format("%s failed: %s", #expr, cudaGetErrorString(_e)));   \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc((void**)&p, count * sizeof(T));
+  }
+};
+
+struct Shard {
+  int dev = 0;  // index into ctx->devs
+  uint64_t col0 = 0, n_cols = 0;
+  DevBuf<chrom_single_col> scols;
+  DevBuf<chrom_multi_col> mcols;
+  DevBuf<chrom_species> species;
+  DevBuf<double> tables, y0, outlet, snapshots, final_state, summary, ping, pong;
+  DevBuf<long long> status;
+  BatchDev b{};
+  LaunchGeom g;
+  float kernel_ms = 0.f;
+};
+
+// src/models/injection.rs:410-446
+double injection_evaluate(int32_t kind, double p0, double p1, double p2, double t) {
+  switch (kind) {
+    case CHROM_INJ_DIRAC:
+      return (t == p0) ? p1 : 0.0;
+    case CHROM_INJ_GAUSSIAN: {
+      const double distance = (t - p0) / p1;
+      return p2 * std::exp(((-distance) * distance) / 2.0);
+    }
+    case CHROM_INJ_RECTANGLE:
+      return (t >= p0 && t < p1) ? p2 : 0.0;
+    default:
+      return 0.0;
+  }
+}
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+struct chrom_cuda_plan {
+  chrom_cuda_ctx* ctx = nullptr;
+  chrom_run_cfg cfg{};
+  bool multi = false;
+  uint32_t want = 0;
+  uint64_t n_cols = 0, n_out = 0, n_snap = 0;
+  size_t state_len = 0;  // doubles per column state: nz * n_species
+  size_t series = 0;     // outlet series per column: n_species
+  std::vector<std::unique_ptr<Shard>> shards;
+  std::string desc;
+  double h2d_ms = 0.0;
+  uint64_t h2d_bytes = 0;
+};
+
+namespace {
+
+int32_t check_cfg(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, bool multi) {
+  if (!cfg) return fail(ctx, CHROM_ERR_INVALID, "cfg is NULL");
+  if (const char* m = chrom_cuda_validate_cfg(cfg)) return fail(ctx, CHROM_ERR_INVALID, m);
+  if (cfg->method != CHROM_EULER && cfg->method != CHROM_RK4)
+    return fail(ctx, CHROM_ERR_INVALID, format("unknown method %d (0 = Euler, 1 = RK4)", cfg->method));
+  if (cfg->arith != CHROM_ARITH_FAST && cfg->arith != CHROM_ARITH_EXACT)
+    return fail(ctx, CHROM_ERR_INVALID, format("unknown arith mode %d", cfg->arith));
+  if (cfg->n_points < 2)
+    return fail(ctx, CHROM_ERR_INVALID, format("Need at least 2 spatial points, got %u", cfg->n_points));
+  if (!multi && cfg->n_species != 1)
+    return fail(ctx, CHROM_ERR_INVALID, format("single-species entry point needs n_species == 1, got %u", cfg->n_species));
+  if (multi && cfg->n_species < 1)
+    return fail(ctx, CHROM_ERR_INVALID, "Langmuir multi species must have at least one species.");
+  if (cfg->time_steps >= (1ull << 31))
+    return fail(ctx, CHROM_ERR_UNSUPPORTED, "time_steps >= 2^31 is not supported");
+  if (cfg->outlet_stride >= (1ull << 31) || cfg->snapshot_stride >= (1ull << 31))
+    return fail(ctx, CHROM_ERR_UNSUPPORTED, "strides >= 2^31 are not supported");
+  return CHROM_OK;
+}
+
+// Upload + allocate one shard.  `cols_*`/`species` are host pointers for the WHOLE batch.
+int32_t build_shard(chrom_cuda_plan* plan, Shard& sh, const chrom_single_col* scols, const chrom_multi_col* mcols,
+                    const chrom_species* species, const double* inj_tables, uint32_t n_tables, const double* y0) {
+  chrom_cuda_ctx* ctx = plan->ctx;
+  const chrom_run_cfg& cfg = plan->cfg;
+  DeviceState& d = ctx->devs[sh.dev];
+  CUDA_TRY(ctx, cudaSetDevice(d.id));
+  const uint32_t stages = chrom_cuda_table_stages(cfg.method);
+  const size_t table_len = (size_t)n_tables * cfg.time_steps * stages;
+  const size_t state_len = plan->state_len;
+
+  CUDA_TRY(ctx, cudaEventRecord(d.ev[0], d.stream));
+  uint64_t bytes = 0;
+  if (!plan->multi) {
+    CUDA_TRY(ctx, sh.scols.alloc(sh.n_cols));
+    CUDA_TRY(ctx, cudaMemcpyAsync(sh.scols.p, scols + sh.col0, sh.n_cols * sizeof(chrom_single_col),
+                                  cudaMemcpyHostToDevice, d.stream));
+    bytes += sh.n_cols * sizeof(chrom_single_col);
+  } else {
+    // rebase species offsets so the shard owns a dense species array
+    const uint32_t n = cfg.n_species;
+    std::vector<chrom_multi_col> cols(mcols + sh.col0, mcols + sh.col0 + sh.n_cols);
+    std::vector<chrom_species> sp((size_t)sh.n_cols * n);
+    for (uint64_t c = 0; c < sh.n_cols; ++c) {
+      std::memcpy(&sp[c * n], species + cols[c].species_off, n * sizeof(chrom_species));
+      cols[c].species_off = (uint32_t)(c * n);
+    }
+    CUDA_TRY(ctx, sh.mcols.alloc(sh.n_cols));
+    CUDA_TRY(ctx, sh.species.alloc(sp.size()));
+    // synchronous copies: the staging vectors die at scope exit
+    CUDA_TRY(ctx, cudaMemcpy(sh.mcols.p, cols.data(), cols.size() * sizeof(chrom_multi_col), cudaMemcpyHostToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(sh.species.p, sp.data(), sp.size() * sizeof(chrom_species), cudaMemcpyHostToDevice));
+    bytes += cols.size() * sizeof(chrom_multi_col) + sp.size() * sizeof(chrom_species);
+  }
+  CUDA_TRY(ctx, sh.tables.alloc(table_len));
+  CUDA_TRY(ctx, cudaMemcpyAsync(sh.tables.p, inj_tables, table_len * sizeof(double), cudaMemcpyHostToDevice, d.stream));
+  bytes += table_len * sizeof(double);
+  if (y0) {
+    CUDA_TRY(ctx, sh.y0.alloc(sh.n_cols * state_len));
+    CUDA_TRY(ctx, cudaMemcpyAsync(sh.y0.p, y0 + sh.col0 * state_len, sh.n_cols * state_len * sizeof(double),
+                                  cudaMemcpyHostToDevice, d.stream));
+    bytes += sh.n_cols * state_len * sizeof(double);
+  }
+  CUDA_TRY(ctx, cudaEventRecord(d.ev[1], d.stream));
+  plan->h2d_bytes += bytes;
+
+  const uint32_t want = plan->want;
+  if ((want & CHROM_WANT_OUTLET) && plan->n_out) CUDA_TRY(ctx, sh.outlet.alloc(sh.n_cols * plan->series * plan->n_out));
+  if ((want & CHROM_WANT_SNAPSHOTS) && plan->n_snap) CUDA_TRY(ctx, sh.snapshots.alloc(sh.n_cols * plan->n_snap * state_len));
+  if (want & CHROM_WANT_FINAL) CUDA_TRY(ctx, sh.final_state.alloc(sh.n_cols * state_len));
+  if (want & CHROM_WANT_SUMMARY) CUDA_TRY(ctx, sh.summary.alloc(sh.n_cols * plan->series * 4));
+  CUDA_TRY(ctx, sh.status.alloc(sh.n_cols));  // always kept: validate_state is part of the solve
+
+  BatchDev& b = sh.b;
+  b.scols = sh.scols.p;
+  b.mcols = sh.mcols.p;
+  b.species = sh.species.p;
+  b.tables = sh.tables.p;
+  b.y0 = sh.y0.p;
+  b.outlet = sh.outlet.p;
+  b.snapshots = sh.snapshots.p;
+  b.final_state = sh.final_state.p;
+  b.summary = sh.summary.p;
+  b.status = sh.status.p;
+  b.ping = b.pong = nullptr;
+  b.n_cols = (uint32_t)sh.n_cols;
+  b.nz = cfg.n_points;
+  b.n_species = cfg.n_species;
+  b.steps = (uint32_t)cfg.time_steps;
+  b.stages = stages;
+  b.outlet_stride = sh.outlet.p ? (uint32_t)cfg.outlet_stride : 0u;
+  b.snapshot_stride = sh.snapshots.p ? (uint32_t)cfg.snapshot_stride : 0u;
+  b.n_out = (uint32_t)plan->n_out;
+  b.n_snap = (uint32_t)plan->n_snap;
+  b.method = cfg.method;
+  b.arith = cfg.arith;
+  // rk4.rs:238 `dt = total_time / (time_steps as f64)`, :284 `dt / 2.0`, :311 `dt / 6.0`
+  b.dt = cfg.total_time / (double)cfg.time_steps;
+  b.half_dt = b.dt / 2.0;
+  b.sixth_dt = b.dt / 6.0;
+
+  std::string why;
+  bool ok = false;
+  if (!plan->multi) {
+    ok = single_resident_choose(b, d.sm_count, &sh.g, &why);
+    if (!ok) ok = single_stream_choose(b, d.sm_count, &sh.g, &why);
+    if (ok && sh.g.kind == 3) {
+      CUDA_TRY(ctx, sh.ping.alloc(sh.n_cols * state_len));
+      CUDA_TRY(ctx, sh.pong.alloc(sh.n_cols * state_len));
+      b.ping = sh.ping.p;
+      b.pong = sh.pong.p;
+    }
+  } else {
+    ok = multi_resident_choose(b, d.sm_count, &sh.g, &why);
+  }
+  if (!ok) return fail(ctx, CHROM_ERR_UNSUPPORTED, "no kernel covers this shape: " + why);
+  return CHROM_OK;
+}
+
+int32_t make_plan(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, bool multi, const chrom_single_col* scols,
+                  const chrom_multi_col* mcols, uint64_t n_cols, const chrom_species* species,
+                  uint64_t n_species_total, const double* inj_tables, uint32_t n_tables, const double* y0,
+                  uint32_t want, chrom_cuda_plan** out) {
+  if (!ctx) return fail(nullptr, CHROM_ERR_INVALID, "ctx is NULL");
+  if (!out) return fail(ctx, CHROM_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (int32_t rc = check_cfg(ctx, cfg, multi)) return rc;
+  if (n_cols == 0) return fail(ctx, CHROM_ERR_INVALID, "n_cols must be > 0");
+  if (n_cols > 0x7fffffffull) return fail(ctx, CHROM_ERR_UNSUPPORTED, "n_cols > 2^31-1 is not supported");
+  if ((!multi && !scols) || (multi && (!mcols || !species)))
+    return fail(ctx, CHROM_ERR_INVALID, "column / species descriptors are NULL");
+  if (!inj_tables || n_tables == 0) return fail(ctx, CHROM_ERR_INVALID, "inj_tables is NULL / n_tables == 0");
+  const uint32_t n = cfg->n_species;
+  if (!multi) {
+    for (uint64_t c = 0; c < n_cols; ++c)
+      if (scols[c].inj_table >= n_tables)
+        return fail(ctx, CHROM_ERR_INVALID, format("column %llu: inj_table %u >= n_tables %u",
+                                                   (unsigned long long)c, scols[c].inj_table, n_tables));
+  } else {
+    for (uint64_t c = 0; c < n_cols; ++c) {
+      if ((uint64_t)mcols[c].species_off + n > n_species_total)
+        return fail(ctx, CHROM_ERR_INVALID, format("column %llu: species range exceeds n_species_total", (unsigned long long)c));
+      for (uint32_t k = 0; k < n; ++k)
+        if (species[mcols[c].species_off + k].inj_table >= n_tables)
+          return fail(ctx, CHROM_ERR_INVALID, format("column %llu species %u: inj_table >= n_tables", (unsigned long long)c, k));
+    }
+  }
+
+  std::unique_ptr<chrom_cuda_plan> plan(new chrom_cuda_plan);
+  plan->ctx = ctx;
+  plan->cfg = *cfg;
+  plan->multi = multi;
+  plan->want = want;
+  plan->n_cols = n_cols;
+  plan->n_out = chrom_cuda_n_samples(cfg->time_steps, cfg->outlet_stride);
+  plan->n_snap = chrom_cuda_n_samples(cfg->time_steps, cfg->snapshot_stride);
+  plan->state_len = (size_t)cfg->n_points * n;
+  plan->series = n;
+
+  const uint64_t G = ctx->devs.size();
+  const uint64_t per = (n_cols + G - 1) / G;
+  const double t0 = now_ms();
+  for (uint64_t gidx = 0; gidx < G; ++gidx) {
+    const uint64_t c0 = gidx * per;
+    if (c0 >= n_cols) break;
+    std::unique_ptr<Shard> sh(new Shard);
+    sh->dev = (int)gidx;
+    sh->col0 = c0;
+    sh->n_cols = std::min(per, n_cols - c0);
+    if (int32_t rc = build_shard(plan.get(), *sh, scols, mcols, species, inj_tables, n_tables, y0)) return rc;
+    plan->shards.push_back(std::move(sh));
+  }
+  for (auto& sh : plan->shards) {
+    DeviceState& d = ctx->devs[sh->dev];
+    CUDA_TRY(ctx, cudaSetDevice(d.id));
+    CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+  }
+  plan->h2d_ms = now_ms() - t0;
+  plan->desc = plan->shards[0]->g.name;
+  if (plan->shards.size() > 1) plan->desc += format(" x%zu devices", plan->shards.size());
+  *out = plan.release();
+  return CHROM_OK;
+}
+
+int32_t launch_shard(chrom_cuda_ctx* ctx, Shard& sh, cudaStream_t s) {
+  cudaError_t e = cudaSuccess;
+  switch (sh.g.kind) {
+    case 1:
+    case 2:
+      e = single_resident_launch(sh.b, sh.g, s);
+      break;
+    case 3:
+      e = single_stream_launch(sh.b, sh.g, s);
+      break;
+    case 4:
+    case 5:
+      e = multi_resident_launch(sh.b, sh.g, s);
+      break;
+    default:
+      return fail(ctx, CHROM_ERR_UNSUPPORTED, "plan has no kernel");
+  }
+  if (e != cudaSuccess) return fail(ctx, CHROM_ERR_CUDA, format("kernel launch failed: %s", cudaGetErrorString(e)));
+  return CHROM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* chrom_cuda_version(void) { return "chrom_cuda 0.1.0 (sm_100a)"; }
+
+int32_t chrom_cuda_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int32_t chrom_cuda_create(const int32_t* device_ids, int32_t n_devices, chrom_cuda_ctx** out) {
+  if (!out) return fail(nullptr, CHROM_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  const int visible = chrom_cuda_device_count();
+  if (visible <= 0)
+    return fail(nullptr, CHROM_ERR_NO_DEVICE, "no CUDA device visible; libchrom_cuda has no CPU fallback");
+  std::vector<int> ids;
+  if (device_ids) {
+    for (int i = 0; i < n_devices; ++i) ids.push_back(device_ids[i]);
+  } else {
+    const int n = (n_devices <= 0) ? visible : n_devices;
+    for (int i = 0; i < n; ++i) ids.push_back(i);
+  }
+  if (ids.empty()) return fail(nullptr, CHROM_ERR_INVALID, "empty device list");
+  std::unique_ptr<chrom_cuda_ctx> ctx(new chrom_cuda_ctx);
+  for (int id : ids) {
+    if (id < 0 || id >= visible)
+      return fail(nullptr, CHROM_ERR_INVALID, format("device id %d out of range (visible: %d)", id, visible));
+    DeviceState d;
+    d.id = id;
+    CUDA_TRY(nullptr, cudaSetDevice(id));
+    cudaDeviceProp prop;
+    CUDA_TRY(nullptr, cudaGetDeviceProperties(&prop, id));
+    if (prop.major < 10)
+      return fail(nullptr, CHROM_ERR_NO_DEVICE,
+                  format("device %d (%s, sm_%d%d) is not a Blackwell sm_100 part; this library ships sm_100a code only",
+                         id, prop.name, prop.major, prop.minor));
+    d.sm_count = prop.multiProcessorCount;
+    CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    for (auto& ev : d.ev) CUDA_TRY(nullptr, cudaEventCreate(&ev));
+    ctx->devs.push_back(d);
+  }
+  *out = ctx.release();
+  return CHROM_OK;
+}
+
+void chrom_cuda_destroy(chrom_cuda_ctx* ctx) {
+  if (!ctx) return;
+  for (auto& d : ctx->devs) {
+    cudaSetDevice(d.id);
+    for (auto& ev : d.ev)
+      if (ev) cudaEventDestroy(ev);
+    if (d.stream) cudaStreamDestroy(d.stream);
+    if (d.flush_buf) cudaFree(d.flush_buf);
+  }
+  delete ctx;
+}
+
+const char* chrom_cuda_last_error(const chrom_cuda_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int32_t chrom_cuda_last_timing(const chrom_cuda_ctx* ctx, chrom_cuda_timing* out) {
+  if (!ctx || !out) return CHROM_ERR_INVALID;
+  *out = ctx->timing;
+  return CHROM_OK;
+}
+
+int32_t chrom_cuda_host_alloc(size_t bytes, void** out) {
+  if (!out) return CHROM_ERR_INVALID;
+  *out = nullptr;
+  if (cudaHostAlloc(out, bytes, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return CHROM_ERR_CUDA;
+  }
+  return CHROM_OK;
+}
+
+void chrom_cuda_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ---- host helpers ---------------------------------------------------------------------------
+
+const char* chrom_cuda_validate_cfg(const chrom_run_cfg* cfg) {
+  // SolverType::validate, TimeEvolution arm — src/solver/traits.rs:172-185 (same comparisons).
+  if (cfg->total_time <= 0.0) return "Total time must be positive";
+  if (cfg->time_steps == 0) return "TimeSteps must be greater than 0";
+  return nullptr;
+}
+
+uint64_t chrom_cuda_n_samples(uint64_t time_steps, uint64_t stride) { return stride == 0 ? 0 : time_steps / stride + 1; }
+
+void chrom_cuda_time_points(double total_time, uint64_t time_steps, double* out) {
+  const double dt = total_time / (double)time_steps;
+  out[0] = 0.0;                                                                   // rk4.rs:254
+  for (uint64_t s = 0; s < time_steps; ++s) out[s + 1] = ((double)s + 1.0) * dt;  // rk4.rs:327
+}
+
+uint32_t chrom_cuda_table_stages(int32_t method) { return method == CHROM_RK4 ? 3u : 1u; }
+
+int32_t chrom_cuda_tabulate_injection(int32_t kind, double p0, double p1, double p2, int32_t method, double total_time,
+                                      uint64_t time_steps, double* out) {
+  if (!out || time_steps == 0) return CHROM_ERR_INVALID;
+  if (kind < CHROM_INJ_NONE || kind > CHROM_INJ_RECTANGLE) return CHROM_ERR_INVALID;
+  const double dt = total_time / (double)time_steps;
+  if (method == CHROM_RK4) {
+    for (uint64_t step = 0; step < time_steps; ++step) {
+      const double t = (double)step * dt;                                     // rk4.rs:267
+      out[step * 3 + 0] = injection_evaluate(kind, p0, p1, p2, t);            // ctx1: t
+      out[step * 3 + 1] = injection_evaluate(kind, p0, p1, p2, t + dt / 2.0);  // ctx2, ctx3: t + dt/2.0
+      out[step * 3 + 2] = injection_evaluate(kind, p0, p1, p2, t + dt);        // ctx4: t + dt
+    }
+  } else if (method == CHROM_EULER) {
+    for (uint64_t step = 0; step < time_steps; ++step)
+      out[step] = injection_evaluate(kind, p0, p1, p2, dt * (double)step);  // euler.rs:229
+  } else {
+    return CHROM_ERR_INVALID;
+  }
+  return CHROM_OK;
+}
+
+size_t chrom_cuda_status_message(int64_t status, char* buf, size_t buf_len) {
+  if (status == 0) {
+    if (buf && buf_len) buf[0] = '\0';
+    return 0;
+  }
+  std::string m;
+  if (status > 0)
+    m = format("NaN detected in Concentration at step %lld. This indicates numerical instability. "
+               "Try reducing time step (increase time_steps parameter).", (long long)status);
+  else
+    m = format("Infinity detected in Concentration at step %lld. This indicates numerical overflow. "
+               "Try reducing time step or check physics model for division by zero.", (long long)-status);
+  if (buf && buf_len) {
+    const size_t k = std::min(buf_len - 1, m.size());
+    std::memcpy(buf, m.data(), k);
+    buf[k] = '\0';
+  }
+  return m.size();
+}
+
+// ---- plans ------------------------------------------------------------------------------------
+
+int32_t chrom_cuda_plan_single(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, const chrom_single_col* cols,
+                               uint64_t n_cols, const double* inj_tables, uint32_t n_tables, const double* y0,
+                               uint32_t want, chrom_cuda_plan** out) {
+  return make_plan(ctx, cfg, false, cols, nullptr, n_cols, nullptr, 0, inj_tables, n_tables, y0, want, out);
+}
+
+int32_t chrom_cuda_plan_multi(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, const chrom_multi_col* cols,
+                              uint64_t n_cols, const chrom_species* species, uint64_t n_species_total,
+                              const double* inj_tables, uint32_t n_tables, const double* y0, uint32_t want,
+                              chrom_cuda_plan** out) {
+  return make_plan(ctx, cfg, true, nullptr, cols, n_cols, species, n_species_total, inj_tables, n_tables, y0, want, out);
+}
+
+int32_t chrom_cuda_plan_execute(chrom_cuda_plan* plan) {
+  if (!plan) return CHROM_ERR_INVALID;
+  chrom_cuda_ctx* ctx = plan->ctx;
+  const double t0 = now_ms();
+  uint64_t launches = 0;
+  for (auto& sh : plan->shards) {
+    DeviceState& d = ctx->devs[sh->dev];
+    CUDA_TRY(ctx, cudaSetDevice(d.id));
+    CUDA_TRY(ctx, cudaMemsetAsync(sh->status.p, 0, sh->n_cols * sizeof(long long), d.stream));
+    CUDA_TRY(ctx, cudaEventRecord(d.ev[2], d.stream));
+    if (int32_t rc = launch_shard(ctx, *sh, d.stream)) return rc;
+    CUDA_TRY(ctx, cudaEventRecord(d.ev[3], d.stream));
+    launches += sh->g.launches_per_execute;
+  }
+  float kmax = 0.f;
+  for (auto& sh : plan->shards) {
+    DeviceState& d = ctx->devs[sh->dev];
+    CUDA_TRY(ctx, cudaSetDevice(d.id));
+    CUDA_TRY(ctx, cudaEventSynchronize(d.ev[3]));
+    CUDA_TRY(ctx, cudaEventElapsedTime(&sh->kernel_ms, d.ev[2], d.ev[3]));
+    kmax = std::max(kmax, sh->kernel_ms);
+  }
+  ctx->timing = chrom_cuda_timing{};
+  ctx->timing.kernel_ms = kmax;
+  ctx->timing.kernel_launches = launches;
+  ctx->timing.h2d_ms = plan->h2d_ms;
+  ctx->timing.h2d_bytes = plan->h2d_bytes;
+  ctx->timing.total_ms = now_ms() - t0;
+  return CHROM_OK;
+}
+
+int32_t chrom_cuda_plan_download(chrom_cuda_plan* plan, double* outlet, double* snapshots, double* final_state,
+                                 double* summary, int64_t* status) {
+  if (!plan) return CHROM_ERR_INVALID;
+  chrom_cuda_ctx* ctx = plan->ctx;
+  const double t0 = now_ms();
+  uint64_t bytes = 0;
+  auto copy = [&](Shard& sh, cudaStream_t s, void* host, const void* dev, size_t per_col_bytes) -> cudaError_t {
+    if (!host || !dev) return cudaSuccess;
+    bytes += sh.n_cols * per_col_bytes;
+    return cudaMemcpyAsync((char*)host + sh.col0 * per_col_bytes, dev, sh.n_cols * per_col_bytes,
+                           cudaMemcpyDeviceToHost, s);
+  };
+  for (auto& sh : plan->shards) {
+    DeviceState& d = ctx->devs[sh->dev];
+    CUDA_TRY(ctx, cudaSetDevice(d.id));
+    CUDA_TRY(ctx, copy(*sh, d.stream, outlet, sh->outlet.p, plan->series * plan->n_out * sizeof(double)));
+    CUDA_TRY(ctx, copy(*sh, d.stream, snapshots, sh->snapshots.p, plan->n_snap * plan->state_len * sizeof(double)));
+    CUDA_TRY(ctx, copy(*sh, d.stream, final_state, sh->final_state.p, plan->state_len * sizeof(double)));
+    CUDA_TRY(ctx, copy(*sh, d.stream, summary, sh->summary.p, plan->series * 4 * sizeof(double)));
+    CUDA_TRY(ctx, copy(*sh, d.stream, status, sh->status.p, sizeof(long long)));
+  }
+  for (auto& sh : plan->shards) {
+    DeviceState& d = ctx->devs[sh->dev];
+    CUDA_TRY(ctx, cudaSetDevice(d.id));
+    CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+  }
+  ctx->timing.d2h_ms = now_ms() - t0;
+  ctx->timing.d2h_bytes = bytes;
+  return CHROM_OK;
+}
+
+int32_t chrom_cuda_plan_describe(const chrom_cuda_plan* plan, char* buf, size_t buf_len) {
+  if (!plan || !buf || buf_len == 0) return CHROM_ERR_INVALID;
+  snprintf(buf, buf_len, "%s", plan->desc.c_str());
+  return CHROM_OK;
+}
+
+void chrom_cuda_plan_destroy(chrom_cuda_plan* plan) {
+  if (!plan) return;
+  for (auto& sh : plan->shards) {
+    cudaSetDevice(plan->ctx->devs[sh->dev].id);
+    sh.reset();
+  }
+  delete plan;
+}
+
+// ---- one-shot solves --------------------------------------------------------------------------
+
+static int32_t solve_common(chrom_cuda_ctx* ctx, chrom_cuda_plan* plan, double* outlet, double* snapshots,
+                            double* final_state, double* summary, int64_t* status, double t0) {
+  int32_t rc = chrom_cuda_plan_execute(plan);
+  if (rc == CHROM_OK) rc = chrom_cuda_plan_download(plan, outlet, snapshots, final_state, summary, status);
+  chrom_cuda_plan_destroy(plan);
+  ctx->timing.total_ms = now_ms() - t0;
+  return rc;
+}
+
+static uint32_t want_mask(const chrom_run_cfg* cfg, const double* outlet, const double* snapshots,
+                          const double* final_state, const double* summary) {
+  uint32_t w = CHROM_WANT_STATUS;
+  if (outlet && cfg && cfg->outlet_stride) w |= CHROM_WANT_OUTLET;
+  if (snapshots && cfg && cfg->snapshot_stride) w |= CHROM_WANT_SNAPSHOTS;
+  if (final_state) w |= CHROM_WANT_FINAL;
+  if (summary) w |= CHROM_WANT_SUMMARY;
+  return w;
+}
+
+int32_t chrom_cuda_solve_single_batch(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, const chrom_single_col* cols,
+                                      uint64_t n_cols, const double* inj_tables, uint32_t n_tables, const double* y0,
+                                      double* outlet, double* snapshots, double* final_state, double* summary,
+                                      int64_t* status) {
+  const double t0 = now_ms();
+  chrom_cuda_plan* plan = nullptr;
+  int32_t rc = chrom_cuda_plan_single(ctx, cfg, cols, n_cols, inj_tables, n_tables, y0,
+                                      want_mask(cfg, outlet, snapshots, final_state, summary), &plan);
+  if (rc != CHROM_OK) return rc;
+  return solve_common(ctx, plan, outlet, snapshots, final_state, summary, status, t0);
+}
+
+int32_t chrom_cuda_solve_multi_batch(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, const chrom_multi_col* cols,
+                                     uint64_t n_cols, const chrom_species* species, uint64_t n_species_total,
+                                     const double* inj_tables, uint32_t n_tables, const double* y0, double* outlet,
+                                     double* snapshots, double* final_state, double* summary, int64_t* status) {
+  const double t0 = now_ms();
+  chrom_cuda_plan* plan = nullptr;
+  int32_t rc = chrom_cuda_plan_multi(ctx, cfg, cols, n_cols, species, n_species_total, inj_tables, n_tables, y0,
+                                     want_mask(cfg, outlet, snapshots, final_state, summary), &plan);
+  if (rc != CHROM_OK) return rc;
+  return solve_common(ctx, plan, outlet, snapshots, final_state, summary, status, t0);
+}
+
+// ---- measurement ------------------------------------------------------------------------------
+
+int32_t chrom_cuda_measure_fp64_peak(chrom_cuda_ctx* ctx, int32_t device_index, double* tflops, double* ms) {
+  if (!ctx || !tflops || !ms || device_index < 0 || device_index >= (int)ctx->devs.size()) return CHROM_ERR_INVALID;
+  DeviceState& d = ctx->devs[device_index];
+  CUDA_TRY(ctx, cudaSetDevice(d.id));
+  CUDA_TRY(ctx, measure_fp64_peak(d.sm_count, d.stream, tflops, ms));
+  return CHROM_OK;
+}
+
+int32_t chrom_cuda_flush_l2(chrom_cuda_ctx* ctx) {
+  if (!ctx) return CHROM_ERR_INVALID;
+  const size_t bytes = (size_t)256 << 20;
+  for (auto& d : ctx->devs) {
+    CUDA_TRY(ctx, cudaSetDevice(d.id));
+    if (!d.flush_buf) CUDA_TRY(ctx, cudaMalloc(&d.flush_buf, bytes));
+    CUDA_TRY(ctx, cudaMemsetAsync(d.flush_buf, 0x5a, bytes, d.stream));
+  }
+  for (auto& d : ctx->devs) {
+    CUDA_TRY(ctx, cudaSetDevice(d.id));
+    CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+  }
+  return CHROM_OK;
+}
+
+int32_t chrom_cuda_measure_copy_bw(chrom_cuda_ctx* ctx, int32_t device_index, size_t bytes, double* gbs) {
+  if (!ctx || !gbs || device_index < 0 || device_index >= (int)ctx->devs.size()) return CHROM_ERR_INVALID;
+  DeviceState& d = ctx->devs[device_index];
+  CUDA_TRY(ctx, cudaSetDevice(d.id));
+  CUDA_TRY(ctx, measure_copy_bw(bytes, d.stream, gbs));
+  return CHROM_OK;
+}
+
+int32_t chrom_cuda_probe_rcp(chrom_cuda_ctx* ctx, double lo, double hi, uint32_t n, double* max_rel_err) {
+  if (!ctx || !max_rel_err || n == 0) return CHROM_ERR_INVALID;
+  DeviceState& d = ctx->devs[0];
+  CUDA_TRY(ctx, cudaSetDevice(d.id));
+  CUDA_TRY(ctx, probe_rcp(lo, hi, n, d.stream, max_rel_err));
+  return CHROM_OK;
+}
+
+}  // extern "C"

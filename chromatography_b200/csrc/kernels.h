@@ -1,0 +1,71 @@
+// kernels.h — launch descriptors shared by the C-ABI layer (api.cu) and the kernel files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/chrom_cuda.h"
+
+namespace chrom {
+
+// Everything one device shard of a batch needs; all pointers are device pointers.
+struct BatchDev {
+  // inputs
+  const chrom_single_col* scols;  // single-species columns (or null)
+  const chrom_multi_col* mcols;   // multi-species columns (or null)
+  const chrom_species* species;   // species table, indices already rebased to this shard
+  const double* tables;           // [n_tables][steps][stages]
+  const double* y0;               // initial state or null (= zeros)
+  // outputs (any may be null)
+  double* outlet;
+  double* snapshots;
+  double* final_state;
+  double* summary;
+  long long* status;
+  // streaming path scratch: two state buffers [n_cols][nz]
+  double* ping;
+  double* pong;
+  // shape
+  uint32_t n_cols;
+  uint32_t nz;
+  uint32_t n_species;
+  uint32_t steps;
+  uint32_t stages;  // table entries per step
+  uint32_t outlet_stride, snapshot_stride;
+  uint32_t n_out, n_snap;
+  int32_t method, arith;
+  double dt, half_dt, sixth_dt;  // dt, dt/2.0, dt/6.0 evaluated on the host in IEEE double
+};
+
+// How a kernel family maps a batch onto the machine; filled by the *_choose functions.
+struct LaunchGeom {
+  int kind = 0;           // 1 single_resident, 2 single_resident_mw, 3 single_stream, 4 multi_resident, 5 multi_warp
+  int M = 0;              // cells per lane
+  int L = 0;              // lanes per column (resident) / threads per column
+  int cpw = 0;            // columns per warp (resident, single warp)
+  int warps_per_col = 0;  // multi-warp resident
+  dim3 grid, block;
+  size_t smem = 0;
+  uint64_t launches_per_execute = 1;
+  std::string name;
+};
+
+// single_resident.cu
+bool single_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why);
+cudaError_t single_resident_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s);
+
+// single_stream.cu — nz beyond the resident capacity: state streamed through HBM/L2, one launch per step
+bool single_stream_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why);
+cudaError_t single_stream_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s);
+
+// multi_resident.cu — LangmuirMulti, per-cell n x n solve
+bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why);
+cudaError_t multi_resident_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s);
+
+// probe.cu
+cudaError_t measure_fp64_peak(int sm_count, cudaStream_t s, double* tflops, double* ms);
+cudaError_t measure_copy_bw(size_t bytes, cudaStream_t s, double* gbs);
+cudaError_t probe_rcp(double lo, double hi, uint32_t n, cudaStream_t s, double* max_rel_err);
+
+}  // namespace chrom

@@ -1,0 +1,437 @@
+// single_resident.cu — register-resident LangmuirSingle time integrator (RK4 / Euler).
+//
+// Replaces, for a whole batch of columns and ALL time steps in one launch:
+//   RK4Solver::solve / EulerSolver::solve   src/solver/methods/rk4.rs:266-332, euler.rs:227-269
+//   LangmuirSingle::compute_physics          src/models/langmuir_single.rs:445-516
+//   PhysicalState Add / Mul<f64>             src/physics/traits.rs:454-491
+//   validate_state                           src/solver/mod.rs:514-553
+//
+// Layout: a column of nz cells is cut into L contiguous chunks of M cells; lane p of the column
+// owns cells [p*M, p*M+M) in registers (y = state at t_n, u = current stage state, acc = running
+// weighted slope).  The upwind neighbour of a lane's first cell is the previous lane's last cell:
+// one 64-bit shuffle per lane per stage; the column's first lane takes the tabulated inlet value.
+// A warp carries cpw = 32/L columns (L need not divide 32; spare lanes idle).  When a column
+// needs more than one warp (MW) the warp-boundary value crosses through shared memory with one
+// __syncthreads per stage.  HBM is touched for: parameters + y0 (once), the inlet table (3 doubles
+// per step, L1/L2 resident), sampled outputs, final state.
+//
+// In-place stage update: cells are visited in DESCENDING order, so u[j-1] is still the current
+// stage's value when cell j reads it, and u[j] can be overwritten with the next stage's state at once.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "arith.cuh"
+#include "kernels.h"
+
+namespace chrom {
+namespace {
+
+template <bool EXACT>
+struct Coef;
+
+// EXACT: langmuir_single.rs:391-396, 409-412, 503-510, one IEEE op per reference op.
+template <>
+struct Coef<true> {
+  double K, nK, lambda, fe, ue, dz;
+  __device__ __forceinline__ void init(const chrom_single_col& c) {
+    // n_bar = fe / (1.0 + fe) * port_number is loop-invariant: hoisting it gives the same bits.
+    const double n_bar = x_mul(x_div(c.fe, x_add(1.0, c.fe)), c.port_number);
+    K = c.langmuir_k;
+    nK = x_mul(n_bar, c.langmuir_k);
+    lambda = c.lambda;
+    fe = c.fe;
+    ue = c.ue;
+    dz = c.dz;
+  }
+  __device__ __forceinline__ double rhs(double c, double up) const {
+    const double denom = x_add(1.0, x_mul(K, c));
+    const double deriv = x_add(lambda, x_div(nK, x_mul(denom, denom)));
+    const double sigma = x_div(1.0, x_add(1.0, x_mul(fe, deriv)));
+    const double dc_dz = x_div(x_sub(c, up), dz);
+    return x_mul(x_mul(-sigma, ue), dc_dz);
+  }
+  static __device__ __forceinline__ double axpy(double y, double k, double h) { return x_add(y, x_mul(k, h)); }
+  static __device__ __forceinline__ double add(double a, double b) { return x_add(a, b); }
+};
+
+// FAST: sigma*(-ue/dz)*(c-up) = (c-up)*d2 / (A'*d2 + B'),  d = 1+K*c, d2 = d*d,
+//       A' = (1+fe*lambda)/Cg, B' = fe*n_bar*K/Cg, Cg = -ue/dz.   9 DFMA-pipe ops + 1 MUFU.
+template <>
+struct Coef<false> {
+  double K, Ap, Bp;
+  __device__ __forceinline__ void init(const chrom_single_col& c) {
+    const double n_bar = c.fe / (1.0 + c.fe) * c.port_number;
+    const double A = 1.0 + c.fe * c.lambda;
+    const double B = c.fe * (n_bar * c.langmuir_k);
+    const double Cg = -c.ue / c.dz;
+    K = c.langmuir_k;
+    Ap = A / Cg;
+    Bp = B / Cg;
+  }
+  __device__ __forceinline__ double rhs(double c, double up) const {
+    const double d = fma(K, c, 1.0);
+    const double d2 = d * d;
+    const double den = fma(Ap, d2, Bp);
+    const double r = fast_rcp(den);
+    const double g = c - up;
+    return (g * d2) * r;
+  }
+  static __device__ __forceinline__ double axpy(double y, double k, double h) { return fma(k, h, y); }
+  static __device__ __forceinline__ double add(double a, double b) { return a + b; }
+};
+
+constexpr int kBlockThreads = 64;  // single-warp-per-column variant: 2 independent warps per CTA
+
+constexpr int min_blocks_for(int M) { return M >= 17 ? 4 : (M >= 11 ? 6 : 8); }
+// multi-warp variant: threads per CTA the register file allows for M cells per lane
+constexpr int mw_max_threads(int M) { return M <= 8 ? 512 : 256; }
+
+template <int M, int METHOD, bool EXACT, bool MW>
+__global__ void __launch_bounds__(MW ? mw_max_threads(M) : kBlockThreads, MW ? 1 : min_blocks_for(M))
+    k_single_resident(const BatchDev b, const int L, const int cpw) {
+  constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
+  using Q = Coef<EXACT>;
+  __shared__ double halo[2][32];
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  int p;
+  uint32_t col;
+  bool active;
+  unsigned gmask;  // lanes of this lane's column (single-warp variant)
+  if (MW) {
+    col = blockIdx.x;
+    p = threadIdx.x;
+    active = true;
+    gmask = 0xffffffffu;
+  } else {
+    const uint32_t gw = blockIdx.x * (kBlockThreads / 32) + warp;
+    const int sub = lane / L;
+    p = lane - sub * L;
+    col = gw * cpw + sub;
+    active = (sub < cpw) && (col < b.n_cols);
+    gmask = (L >= 32) ? 0xffffffffu : (((1u << L) - 1u) << (sub * L));
+  }
+  const uint32_t colc = active ? col : 0u;
+  const uint32_t nz = b.nz;
+  const chrom_single_col cp = b.scols[colc];
+  Q q;
+  q.init(cp);
+
+  const int cell0 = p * M;
+  const int nv = max(0, min(M, (int)nz - cell0));  // real cells on this lane
+  const int p_out = (int)(nz - 1) / M;
+  const int j_out = (int)(nz - 1) - p_out * M;
+  const bool out_lane = active && (p == p_out);
+
+  double y[M], u[M], acc[M];
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    y[j] = (b.y0 != nullptr && j < nv) ? b.y0[(size_t)colc * nz + cell0 + j] : 0.0;
+    u[j] = 0.0;
+    acc[j] = 0.0;
+  }
+
+  const double dt = b.dt, h2 = b.half_dt, h6 = b.sixth_dt;
+  const uint32_t steps = b.steps;
+  const double* __restrict__ tab = b.tables + (size_t)cp.inj_table * steps * ST;
+
+  auto outlet_value = [&]() -> double {
+    double v = y[M - 1];
+    if (j_out != M - 1) {
+#pragma unroll
+      for (int j = 0; j < M - 1; ++j) v = (j == j_out) ? y[j] : v;
+    }
+    return v;
+  };
+  auto store_profile = [&](double* dst) {  // dst -> this column's [nz] slot
+#pragma unroll
+    for (int j = 0; j < M; ++j)
+      if (j < nv) dst[cell0 + j] = y[j];
+  };
+
+  // step 0 samples (initial condition: rk4.rs:254-255)
+  double v_prev = 0.0, s_area = 0.0, s_mom = 0.0, s_max = 0.0, s_tmax = 0.0;
+  {
+    const double v0 = outlet_value();
+    v_prev = v0;
+    s_max = v0;
+    if (out_lane && b.outlet) b.outlet[(size_t)col * b.n_out] = v0;
+    if (active && b.snapshots) store_profile(b.snapshots + (size_t)col * b.n_snap * nz);
+  }
+  uint32_t out_count = b.outlet_stride, snap_count = b.snapshot_stride;
+  uint32_t out_slot = 1, snap_slot = 1;
+  bool done = false;
+
+  double n0 = 0.0, n1 = 0.0, n2 = 0.0;
+  n0 = tab[0];
+  if (ST == 3) {
+    n1 = tab[1];
+    n2 = tab[2];
+  }
+
+  // upwind value for the first cell of this lane at the current stage
+  auto exchange = [&](double last, double inlet, int parity) -> double {
+    double up = __shfl_up_sync(0xffffffffu, last, 1);
+    if (MW) {
+      if (lane == 31) halo[parity][warp] = last;
+      __syncthreads();
+      if (lane == 0 && warp > 0) up = halo[parity][warp - 1];
+    }
+    return (p == 0) ? inlet : up;
+  };
+
+  for (uint32_t step = 0; step < steps; ++step) {
+    const double cin0 = n0, cin1 = n1, cin2 = n2;
+    if (step + 1 < steps) {  // prefetch the next step's inlet values
+      const double* nx = tab + (size_t)(step + 1) * ST;
+      n0 = nx[0];
+      if (ST == 3) {
+        n1 = nx[1];
+        n2 = nx[2];
+      }
+    }
+
+    if (METHOD == CHROM_RK4) {
+      // stage 1: k1 = f(y, t)            acc = k1            u = y + k1*(dt/2)
+      double up = exchange(y[M - 1], cin0, 0);
+#pragma unroll
+      for (int j = M - 1; j >= 0; --j) {
+        const double k = q.rhs(y[j], j > 0 ? y[j - 1] : up);
+        acc[j] = k;
+        u[j] = Q::axpy(y[j], k, h2);
+      }
+      // stage 2: k2 = f(u, t+dt/2)       acc = acc + k2*2    u = y + k2*(dt/2)
+      up = exchange(u[M - 1], cin1, 1);
+#pragma unroll
+      for (int j = M - 1; j >= 0; --j) {
+        const double k = q.rhs(u[j], j > 0 ? u[j - 1] : up);
+        acc[j] = Q::axpy(acc[j], k, 2.0);
+        u[j] = Q::axpy(y[j], k, h2);
+      }
+      // stage 3: k3 = f(u, t+dt/2)       acc = acc + k3*2    u = y + k3*dt
+      up = exchange(u[M - 1], cin1, 0);
+#pragma unroll
+      for (int j = M - 1; j >= 0; --j) {
+        const double k = q.rhs(u[j], j > 0 ? u[j - 1] : up);
+        acc[j] = Q::axpy(acc[j], k, 2.0);
+        u[j] = Q::axpy(y[j], k, dt);
+      }
+      // stage 4: k4 = f(u, t+dt)         y = y + (acc + k4)*(dt/6)
+      up = exchange(u[M - 1], cin2, 1);
+#pragma unroll
+      for (int j = M - 1; j >= 0; --j) {
+        const double k = q.rhs(u[j], j > 0 ? u[j - 1] : up);
+        y[j] = Q::axpy(y[j], Q::add(acc[j], k), h6);
+      }
+    } else {
+      // forward Euler: y = y + f(y, t)*dt
+      const double up = exchange(y[M - 1], cin0, (int)(step & 1u));
+#pragma unroll
+      for (int j = M - 1; j >= 0; --j) {
+        const double k = q.rhs(y[j], j > 0 ? y[j - 1] : up);
+        y[j] = Q::axpy(y[j], k, dt);
+      }
+    }
+
+    // ---- samples ------------------------------------------------------------------------
+    const bool want_out = (b.outlet != nullptr) && (--out_count == 0);
+    if (b.summary != nullptr || want_out) {
+      const double v = outlet_value();
+      if (want_out) {
+        out_count = b.outlet_stride;
+        if (out_lane) b.outlet[(size_t)col * b.n_out + out_slot] = v;
+        ++out_slot;
+      }
+      if (b.summary != nullptr && out_lane) {
+        const double t0 = (double)step * dt, t1 = ((double)step + 1.0) * dt;
+        const double w = 0.5 * (t1 - t0);
+        s_area = fma(w, v_prev + v, s_area);
+        s_mom = fma(w, fma(t0, v_prev, t1 * v), s_mom);
+        if (v > s_max) {
+          s_max = v;
+          s_tmax = t1;
+        }
+        v_prev = v;
+      }
+    }
+    if (b.snapshots != nullptr && --snap_count == 0) {
+      snap_count = b.snapshot_stride;
+      if (active) store_profile(b.snapshots + ((size_t)col * b.n_snap + snap_slot) * nz);
+      ++snap_slot;
+    }
+
+    // ---- validate_state (solver/mod.rs:514-553) on the integer pipe -------------------------
+    unsigned mx = 0u;
+#pragma unroll
+    for (int j = 0; j < M; ++j) mx = max(mx, j < nv ? abs_hi(y[j]) : 0u);
+    const bool bad = active && hi_nonfinite(mx);
+    if (MW) {
+      if (__syncthreads_or(bad) && !done) {
+        bool has_nan = false;
+#pragma unroll
+        for (int j = 0; j < M; ++j) has_nan |= (j < nv) && (y[j] != y[j]);
+        const int any_nan = __syncthreads_or(has_nan);
+        if (threadIdx.x == 0 && b.status)
+          b.status[col] = any_nan ? (long long)(step + 1) : -(long long)(step + 1);
+        done = true;
+      }
+    } else {
+      const unsigned ballot = __ballot_sync(0xffffffffu, bad);
+      if (ballot != 0u) {
+        bool has_nan = false;
+#pragma unroll
+        for (int j = 0; j < M; ++j) has_nan |= (j < nv) && (y[j] != y[j]);
+        const unsigned nan_ballot = __ballot_sync(0xffffffffu, has_nan && active);
+        if ((ballot & gmask) != 0u && !done) {
+          if (p == 0 && active && b.status)
+            b.status[col] = (nan_ballot & gmask) ? (long long)(step + 1) : -(long long)(step + 1);
+          done = true;
+        }
+      }
+    }
+  }
+
+  if (active && b.final_state) store_profile(b.final_state + (size_t)col * nz);
+  if (out_lane && b.summary) {
+    double* s = b.summary + (size_t)col * 4;
+    s[0] = s_area;
+    s[1] = (s_area != 0.0) ? s_mom / s_area : 0.0;
+    s[2] = s_max;
+    s[3] = s_tmax;
+  }
+}
+
+// ---- instantiation tables -----------------------------------------------------------------
+typedef void (*kern_t)(const BatchDev, const int, const int);
+
+template <int M, bool MW>
+kern_t pick(int method, int arith) {
+  if (method == CHROM_RK4)
+    return arith == CHROM_ARITH_EXACT ? k_single_resident<M, CHROM_RK4, true, MW>
+                                      : k_single_resident<M, CHROM_RK4, false, MW>;
+  return arith == CHROM_ARITH_EXACT ? k_single_resident<M, CHROM_EULER, true, MW>
+                                    : k_single_resident<M, CHROM_EULER, false, MW>;
+}
+
+const int kM[] = {2, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 25, 28, 32};
+const int kMmw[] = {8, 16, 32};
+
+kern_t lookup(int M, bool mw, int method, int arith) {
+  if (mw) {
+    switch (M) {
+      case 8: return pick<8, true>(method, arith);
+      case 16: return pick<16, true>(method, arith);
+      case 32: return pick<32, true>(method, arith);
+    }
+    return nullptr;
+  }
+  switch (M) {
+    case 2: return pick<2, false>(method, arith);
+    case 4: return pick<4, false>(method, arith);
+    case 5: return pick<5, false>(method, arith);
+    case 6: return pick<6, false>(method, arith);
+    case 7: return pick<7, false>(method, arith);
+    case 8: return pick<8, false>(method, arith);
+    case 10: return pick<10, false>(method, arith);
+    case 12: return pick<12, false>(method, arith);
+    case 14: return pick<14, false>(method, arith);
+    case 16: return pick<16, false>(method, arith);
+    case 20: return pick<20, false>(method, arith);
+    case 25: return pick<25, false>(method, arith);
+    case 28: return pick<28, false>(method, arith);
+    case 32: return pick<32, false>(method, arith);
+  }
+  return nullptr;
+}
+
+}  // namespace
+
+// Largest nz the resident path holds (256 threads x 32 cells, 512 x 16, 1024 x 8).
+static const uint32_t kMaxResidentNz = 8192;
+
+bool single_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why) {
+  const uint32_t nz = b.nz;
+  if (nz > kMaxResidentNz) {
+    if (why) *why = "nz exceeds the register-resident capacity (8192 cells per CTA)";
+    return false;
+  }
+  char buf[160];
+  if (nz <= 32u * 32u) {
+    // single warp per column: maximise the fraction of lane-slots doing real cells; when the batch
+    // cannot fill the machine prefer short chunks (more lanes in flight per column).
+    const uint64_t fill_warps = (uint64_t)sm_count * 8u;
+    double best_score = -1.0;
+    int bestM = 0, bestL = 0, bestCpw = 0;
+    const char* force = getenv("CHROM_FORCE_M");  // experiments only
+    for (int M : kM) {
+      if (force && atoi(force) != M) continue;
+      const int L = (int)((nz + M - 1) / M);
+      if (L > 32) continue;
+      const int cpw = 32 / L;
+      const double eff = (double)nz * cpw / (32.0 * M);
+      const uint64_t warps = (b.n_cols + cpw - 1) / cpw;
+      // shuffle + control overhead is amortised over M cells: ~2% per 1/M
+      double score = eff * (1.0 - 0.25 / M);
+      if (warps < fill_warps) score = eff / M;  // latency-bound batch: shortest critical path wins
+      if (score > best_score) {
+        best_score = score;
+        bestM = M;
+        bestL = L;
+        bestCpw = cpw;
+      }
+    }
+    if (bestM == 0) return false;
+    const uint64_t warps = ((uint64_t)b.n_cols + bestCpw - 1) / bestCpw;
+    g->kind = 1;
+    g->M = bestM;
+    g->L = bestL;
+    g->cpw = bestCpw;
+    g->warps_per_col = 1;
+    g->block = dim3(kBlockThreads);
+    g->grid = dim3((unsigned)((warps + (kBlockThreads / 32) - 1) / (kBlockThreads / 32)));
+    g->smem = 0;
+    snprintf(buf, sizeof buf, "single_resident<M=%d,%s,%s> lanes/col=%d cols/warp=%d grid=%u block=%d",
+             bestM, b.method == CHROM_RK4 ? "RK4" : "Euler", b.arith == CHROM_ARITH_EXACT ? "exact" : "fast",
+             bestL, bestCpw, g->grid.x, kBlockThreads);
+    g->name = buf;
+    return true;
+  }
+  // multi-warp per column: one CTA per column, fewest padded cells, then the largest chunk
+  int bestM = 0, bestW = 0;
+  uint32_t best_pad = 0xffffffffu;
+  for (int M : kMmw) {
+    const int W = (int)((nz + 32u * M - 1) / (32u * M));
+    if (W * 32 > mw_max_threads(M)) continue;
+    const uint32_t pad = (uint32_t)W * 32u * M - nz;
+    if (pad <= best_pad) {
+      best_pad = pad;
+      bestM = M;
+      bestW = W;
+    }
+  }
+  if (bestM == 0) return false;
+  g->kind = 2;
+  g->M = bestM;
+  g->L = bestW * 32;
+  g->cpw = 1;
+  g->warps_per_col = bestW;
+  g->block = dim3(bestW * 32);
+  g->grid = dim3(b.n_cols);
+  g->smem = 0;
+  snprintf(buf, sizeof buf, "single_resident_mw<M=%d,%s,%s> warps/col=%d grid=%u block=%d", bestM,
+           b.method == CHROM_RK4 ? "RK4" : "Euler", b.arith == CHROM_ARITH_EXACT ? "exact" : "fast", bestW,
+           g->grid.x, bestW * 32);
+  g->name = buf;
+  return true;
+}
+
+cudaError_t single_resident_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s) {
+  kern_t k = lookup(g.M, g.kind == 2, b.method, b.arith);
+  if (!k) return cudaErrorInvalidValue;
+  k<<<g.grid, g.block, g.smem, s>>>(b, g.L, g.cpw);
+  return cudaGetLastError();
+}
+
+}  // namespace chrom

@@ -1,0 +1,192 @@
+/* chrom_cuda.h — C ABI of libchrom_cuda.so, the B200 (sm_100a) backend for the method-of-lines
+ * time integrator of chrom-rs.  This is the drop-in boundary: everything a Rust `impl Solver`
+ * needs, as `extern "C"` functions over plain pointers and sizes.  No torch / C++ types.
+ *
+ * What each entry point replaces in the reference (paths relative to the chrom-rs tree):
+ *   chrom_cuda_solve_single_batch   RK4Solver::solve / EulerSolver::solve on a LangmuirSingle scenario
+ *                                   src/solver/methods/rk4.rs:205-350, euler.rs:166-288,
+ *                                   src/models/langmuir_single.rs:445-516; one call = n_cols solves
+ *   chrom_cuda_solve_multi_batch    the same solvers on a LangmuirMulti scenario
+ *                                   src/models/langmuir_multi.rs:717-899 (jacobian 627-668, inverse 674-686)
+ *   chrom_cuda_tabulate_injection   TemporalInjection::evaluate at the stage times the solvers use
+ *                                   src/models/injection.rs:410-446; rk4.rs:267,283,289,295; euler.rs:229
+ *   status[]                        validate_state  src/solver/mod.rs:514-553
+ *   chrom_cuda_status_message       the Err(String) texts of src/solver/mod.rs:527-548
+ *   chrom_cuda_validate_cfg         SolverType::validate  src/solver/traits.rs:172-185
+ *   chrom_cuda_time_points          time_points of SimulationResult  rk4.rs:254,327
+ *   plan_* functions                no reference counterpart: keep a batch resident in HBM between calls
+ *
+ * Conventions: every function returns CHROM_OK (0) or a negative CHROM_ERR_*; the text of the last
+ * error on a context is returned by chrom_cuda_last_error.  Buffers are caller-allocated; the
+ * library never keeps or frees caller memory.  A context is not thread-safe; distinct contexts are.
+ * There is no CPU fallback: without a CUDA device chrom_cuda_create fails.
+ */
+#ifndef CHROM_CUDA_H
+#define CHROM_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHROM_OK 0
+#define CHROM_ERR_INVALID (-1)     /* bad argument / configuration (message says which) */
+#define CHROM_ERR_CUDA (-2)        /* CUDA runtime error */
+#define CHROM_ERR_UNSUPPORTED (-3) /* shape outside what the kernels cover */
+#define CHROM_ERR_NO_DEVICE (-4)   /* no usable CUDA device: there is no CPU fallback */
+
+#define CHROM_EULER 0
+#define CHROM_RK4 1
+
+/* Arithmetic mode of the kernels.
+ * FAST  : algebraically reduced RHS (one reciprocal per cell-stage), FMA contraction.  Within
+ *         1e-9 relative of the reference on concentration profiles (typically ~1e-13).
+ * EXACT : every IEEE operation of the reference in the reference's order, no FMA.  Bit-identical
+ *         to the reference arithmetic (n<=4 closed-form inverses and n>=5 nalgebra LU included). */
+#define CHROM_ARITH_FAST 0
+#define CHROM_ARITH_EXACT 1
+
+#define CHROM_INJ_NONE 0
+#define CHROM_INJ_DIRAC 1     /* p0 = time, p1 = amount */
+#define CHROM_INJ_GAUSSIAN 2  /* p0 = center, p1 = width, p2 = peak_concentration */
+#define CHROM_INJ_RECTANGLE 3 /* p0 = start, p1 = end, p2 = concentration */
+
+typedef struct chrom_cuda_ctx chrom_cuda_ctx;
+typedef struct chrom_cuda_plan chrom_cuda_plan;
+
+/* One LangmuirSingle column.  fe, ue, dz are passed verbatim (the reference deserialises them from
+ * the model file and never recomputes them: src/config/model.rs:111-148). */
+typedef struct {
+  double lambda, langmuir_k, port_number, fe, ue, dz;
+  uint32_t inj_table; /* index into inj_tables */
+  uint32_t _reserved;
+} chrom_single_col;
+
+/* One LangmuirMulti column; its species are species[species_off .. species_off + n_species). */
+typedef struct {
+  double fe, ue, dz, stationary_fraction;
+  uint32_t species_off;
+  uint32_t _reserved;
+} chrom_multi_col;
+
+typedef struct {
+  double lambda, langmuir_k;
+  uint32_t port_number;
+  uint32_t inj_table;
+} chrom_species;
+
+typedef struct {
+  int32_t method;           /* CHROM_EULER | CHROM_RK4 */
+  int32_t arith;            /* CHROM_ARITH_FAST | CHROM_ARITH_EXACT */
+  double total_time;        /* > 0 */
+  uint64_t time_steps;      /* > 0; dt = total_time / (double)time_steps */
+  uint32_t n_points;        /* nz >= 2 */
+  uint32_t n_species;       /* 1 for the single-species entry points */
+  uint64_t outlet_stride;   /* outlet sampled at steps 0, k, 2k, ...; 1 = every step (reference); 0 = none */
+  uint64_t snapshot_stride; /* full profile at steps 0, k, 2k, ...; 1 = the whole trajectory; 0 = none */
+} chrom_run_cfg;
+
+typedef struct {
+  double h2d_ms;    /* host->device copies (CUDA events, max over devices) */
+  double kernel_ms; /* solver kernels only, CUDA events on the launch stream, max over devices */
+  double d2h_ms;    /* device->host copies */
+  double total_ms;  /* host wall clock of the whole call */
+  uint64_t kernel_launches;
+  uint64_t h2d_bytes, d2h_bytes;
+} chrom_cuda_timing;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int32_t chrom_cuda_device_count(void);
+/* device_ids == NULL: use devices 0..n_devices-1 (n_devices <= 0: all visible devices). */
+int32_t chrom_cuda_create(const int32_t* device_ids, int32_t n_devices, chrom_cuda_ctx** out);
+void chrom_cuda_destroy(chrom_cuda_ctx* ctx);
+/* Valid until the next call on ctx.  ctx == NULL: the last error of chrom_cuda_create on this thread. */
+const char* chrom_cuda_last_error(const chrom_cuda_ctx* ctx);
+const char* chrom_cuda_version(void);
+int32_t chrom_cuda_last_timing(const chrom_cuda_ctx* ctx, chrom_cuda_timing* out);
+
+/* Page-locked host memory for buffers handed to solve / download (pageable memory works, slower). */
+int32_t chrom_cuda_host_alloc(size_t bytes, void** out);
+void chrom_cuda_host_free(void* p);
+
+/* ---- host-side helpers (pure CPU, no device needed) ------------------------------------------ */
+/* Error text of SolverType::validate; NULL when the configuration is valid. */
+const char* chrom_cuda_validate_cfg(const chrom_run_cfg* cfg);
+/* Number of samples a stride produces: 0 if stride == 0 else time_steps / stride + 1. */
+uint64_t chrom_cuda_n_samples(uint64_t time_steps, uint64_t stride);
+/* out[0] = 0.0, out[s + 1] = ((double)s + 1.0) * dt  — (time_steps + 1) values. */
+void chrom_cuda_time_points(double total_time, uint64_t time_steps, double* out);
+/* Stages per step of a table: 3 for RK4 (t, t + dt/2.0, t + dt), 1 for Euler (t); t = (double)step * dt. */
+uint32_t chrom_cuda_table_stages(int32_t method);
+/* Fills out[time_steps][stages] with TemporalInjection::evaluate at the solver's stage times. */
+int32_t chrom_cuda_tabulate_injection(int32_t kind, double p0, double p1, double p2, int32_t method,
+                                      double total_time, uint64_t time_steps, double* out);
+/* The reference's validate_state error string for a nonzero status (0 bytes written when status == 0).
+ * Returns the length the full message needs. */
+size_t chrom_cuda_status_message(int64_t status, char* buf, size_t buf_len);
+
+/* ---- one-shot solves (host buffers in, host buffers out) ------------------------------------- */
+/* inj_tables : [n_tables][time_steps][stages] host-evaluated inlet concentrations.
+ * y0         : [n_cols][nz] initial state, or NULL = zeros (setup_initial_state).
+ * outlet     : [n_cols][n_out]        last cell at the sampled steps, or NULL
+ * snapshots  : [n_cols][n_snap][nz]   full profiles at the sampled steps, or NULL
+ * final_state: [n_cols][nz]           or NULL
+ * summary    : [n_cols][4]            trapezoid area, first moment (time), max, time of max of the
+ *                                     outlet over all steps, or NULL
+ * status     : [n_cols]               0 ok; +s = NaN first present after step s; -s = Inf (no NaN)
+ *                                     after step s (validate_state runs after every step), or NULL */
+int32_t chrom_cuda_solve_single_batch(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, const chrom_single_col* cols,
+                                      uint64_t n_cols, const double* inj_tables, uint32_t n_tables,
+                                      const double* y0, double* outlet, double* snapshots, double* final_state,
+                                      double* summary, int64_t* status);
+
+/* State layout [n_cols][n_species][nz] (= nalgebra's column-major nz x n matrix per column).
+ * outlet [n_cols][n_species][n_out]; snapshots [n_cols][n_snap][n_species][nz];
+ * final_state [n_cols][n_species][nz]; summary [n_cols][n_species][4]; status [n_cols]. */
+int32_t chrom_cuda_solve_multi_batch(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, const chrom_multi_col* cols,
+                                     uint64_t n_cols, const chrom_species* species, uint64_t n_species_total,
+                                     const double* inj_tables, uint32_t n_tables, const double* y0,
+                                     double* outlet, double* snapshots, double* final_state, double* summary,
+                                     int64_t* status);
+
+/* ---- plans: a batch kept resident in HBM (inputs uploaded once, outputs left on the device) -- */
+#define CHROM_WANT_OUTLET 1u
+#define CHROM_WANT_SNAPSHOTS 2u
+#define CHROM_WANT_FINAL 4u
+#define CHROM_WANT_SUMMARY 8u
+#define CHROM_WANT_STATUS 16u
+
+int32_t chrom_cuda_plan_single(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, const chrom_single_col* cols,
+                               uint64_t n_cols, const double* inj_tables, uint32_t n_tables, const double* y0,
+                               uint32_t want, chrom_cuda_plan** out);
+int32_t chrom_cuda_plan_multi(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, const chrom_multi_col* cols,
+                              uint64_t n_cols, const chrom_species* species, uint64_t n_species_total,
+                              const double* inj_tables, uint32_t n_tables, const double* y0, uint32_t want,
+                              chrom_cuda_plan** out);
+/* Runs the solve from the uploaded initial state; returns after the kernels have finished. */
+int32_t chrom_cuda_plan_execute(chrom_cuda_plan* plan);
+/* Copies the requested outputs to host buffers (any may be NULL). */
+int32_t chrom_cuda_plan_download(chrom_cuda_plan* plan, double* outlet, double* snapshots, double* final_state,
+                                 double* summary, int64_t* status);
+/* Human-readable description of the kernel variant and launch geometry chosen. */
+int32_t chrom_cuda_plan_describe(const chrom_cuda_plan* plan, char* buf, size_t buf_len);
+void chrom_cuda_plan_destroy(chrom_cuda_plan* plan);
+
+/* ---- measurement ----------------------------------------------------------------------------- */
+/* Dependent-free DFMA micro-benchmark on device `device_index` of the context: measured FP64
+ * peak in TFLOP/s (2 flops per DFMA) and the SM clock-independent duration in ms. */
+int32_t chrom_cuda_measure_fp64_peak(chrom_cuda_ctx* ctx, int32_t device_index, double* tflops, double* ms);
+/* Writes a buffer larger than the L2 (256 MiB) on every device of the context: cold-cache timing. */
+int32_t chrom_cuda_flush_l2(chrom_cuda_ctx* ctx);
+/* Device copy bandwidth (read + write bytes / time) in GB/s over `bytes` bytes. */
+int32_t chrom_cuda_measure_copy_bw(chrom_cuda_ctx* ctx, int32_t device_index, size_t bytes, double* gbs);
+/* Max relative error vs IEEE 1.0/x over n samples of +-[lo, hi] of: max_rel_err[0] the MUFU.RCP64H
+ * seed, [1] seed + cubic step, [2] seed + cubic + Newton step (what the FAST kernels use). */
+int32_t chrom_cuda_probe_rcp(chrom_cuda_ctx* ctx, double lo, double hi, uint32_t n, double* max_rel_err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHROM_CUDA_H */
