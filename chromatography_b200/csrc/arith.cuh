@@ -18,9 +18,11 @@ __device__ __forceinline__ double x_div(double a, double b) { return __ddiv_rn(a
 // Seed: rcp.approx.ftz.f64 (SASS MUFU.RCP64H, runs on the XU pipe, not the FP64 pipe).
 // RCP_REFINE = 0: one cubic step   e = 1 - d*x ; x += x*(e + e*e)              (3 DFMA)
 // RCP_REFINE = 1: cubic + one Newton step                                      (5 DFMA)
+// Measured on B200 (chrom_cuda_probe_rcp, 4M samples of +-[1e-3, 1e6]): seed 9.9e-7 (2^-20),
+// cubic 2.2e-16 (<= 1 ulp), cubic+Newton 0 (= IEEE 1/x).  The kernels use the cubic step alone.
 // The operands here are O(1) and far from the subnormal range, so no special-case path.
 #ifndef CHROM_RCP_REFINE
-#define CHROM_RCP_REFINE 1
+#define CHROM_RCP_REFINE 0
 #endif
 
 __device__ __forceinline__ double rcp_seed(double d) {

@@ -217,6 +217,18 @@ class LangmuirMulti:
         return np.array(out, order="C")
 
 
+def from_model(model):
+    """Oracle twin of a host-side model object (duck-typed on the reference's field names, so this
+    module never imports the product package)."""
+    def inj(i):
+        return TemporalInjection(i.kind, i.p0, i.p1, i.p2)
+    if hasattr(model, "species"):
+        sp = [SpeciesParams(s.name, s.lambda_, s.langmuir_k, s.port_number, inj(s.injection)) for s in model.species]
+        return LangmuirMulti(sp, model.n_points, model.fe, model.ue, model.dz, model.stationary_fraction)
+    return LangmuirSingle(model.lambda_, model.langmuir_k, model.port_number, model.fe, model.ue, model.dz,
+                          model.n_points, inj(model.injection))
+
+
 def try_inverse(mat: np.ndarray):
     """nalgebra `try_inverse` restatement.  Returns None when nalgebra would."""
     n = mat.shape[0]

@@ -10,17 +10,8 @@ MOMENT_RTOL = 1e-7    # retention time and peak area
 TINY = 1e-290         # below this both sides are in / next to the subnormal range: compare absolutely
 
 
-def to_oracle_inj(inj: cb.TemporalInjection) -> O.TemporalInjection:
-    return O.TemporalInjection(inj.kind, inj.p0, inj.p1, inj.p2)
-
-
 def to_oracle(model):
-    if isinstance(model, cb.LangmuirSingle):
-        return O.LangmuirSingle(model.lambda_, model.langmuir_k, model.port_number, model.fe, model.ue, model.dz,
-                                model.n_points, to_oracle_inj(model.injection))
-    sp = [O.SpeciesParams(s.name, s.lambda_, s.langmuir_k, s.port_number, to_oracle_inj(s.injection))
-          for s in model.species]
-    return O.LangmuirMulti(sp, model.n_points, model.fe, model.ue, model.dz, model.stationary_fraction)
+    return O.from_model(model)
 
 
 def max_rel_err(a, b) -> float:
