@@ -1,9 +1,566 @@
-// multi_resident.cu — placeholder until the multi-species kernel lands.
+// multi_resident.cu — shared-memory-resident LangmuirMulti time integrator (RK4 / Euler).
+//
+// Replaces, for a batch of columns and ALL time steps in one launch:
+//   RK4Solver::solve / EulerSolver::solve        src/solver/methods/rk4.rs:266-332, euler.rs:227-269
+//   LangmuirMulti::compute_physics / compute_row src/models/langmuir_multi.rs:717-899 (770-840)
+//   LangmuirMulti::jacobian                      src/models/langmuir_multi.rs:627-668
+//   inverse_propagation + `inv * grad`           src/models/langmuir_multi.rs:674-686, 838 (nalgebra 0.34)
+//   validate_state                               src/solver/mod.rs:514-553
+//
+// Layout: one CTA owns one column.  Its state lives in shared memory as [array][species][nz]
+// (species-major, the reference's nalgebra column-major nz x n matrix): y (state at t_n), acc
+// (running weighted slope) and two stage buffers u0/u1 (ping-pong, so a cell may read its upstream
+// neighbour while that neighbour's thread writes the next stage).  One thread processes one cell
+// at a time — all n species — with the n x n matrix I + Fe*M in REGISTERS:
+//   FAST : LU with partial pivoting applied directly to the gradient (no explicit inverse);
+//          pivot search on the integer pipe, row swaps only when some lane of the warp needs one.
+//   EXACT: nalgebra's try_inverse restated operation by operation (closed forms n<=4, partial-pivot
+//          LU + two triangular solves on the permuted identity n>=5), then gemv in nalgebra's order.
+// Cells are strided over threads (cell = tid + c*T): conflict-free shared-memory access.
+// One __syncthreads per stage; the last one of a step carries the non-finite flag.
+#include <algorithm>
+#include <cstdio>
+
+#include "arith.cuh"
 #include "kernels.h"
+
 namespace chrom {
-bool multi_resident_choose(const BatchDev&, int, LaunchGeom*, std::string* why) {
-  if (why) *why = "multi-species path not built yet";
-  return false;
+namespace {
+
+struct SpeciesConst {  // per species, shared memory
+  double lambda, K, nbar;  // nbar = stationary_fraction * (double)port_number
+  double a0;               // FAST: 1 + fe*lambda
+  double feNK;             // FAST: fe * nbar * K
+};
+
+// ------------------------------------------------------------------------------------------------
+// EXACT: nalgebra try_inverse + gemv, column-major a[i + j*N], one IEEE op per reference op.
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__device__ bool exact_try_inverse(const double* m, double* out) {
+  if constexpr (N == 1) {
+    if (m[0] == 0.0) return false;
+    out[0] = x_div(1.0, m[0]);
+    return true;
+  } else if constexpr (N == 2) {
+    const double m11 = m[0], m21 = m[1], m12 = m[2], m22 = m[3];
+    const double det = x_sub(x_mul(m11, m22), x_mul(m21, m12));
+    if (det == 0.0) return false;
+    out[0] = x_div(m22, det);
+    out[2] = x_div(-m12, det);
+    out[1] = x_div(-m21, det);
+    out[3] = x_div(m11, det);
+    return true;
+  } else if constexpr (N == 3) {
+    const double m11 = m[0], m21 = m[1], m31 = m[2], m12 = m[3], m22 = m[4], m32 = m[5], m13 = m[6], m23 = m[7],
+                 m33 = m[8];
+    const double minor_m12_m23 = x_sub(x_mul(m22, m33), x_mul(m32, m23));
+    const double minor_m11_m23 = x_sub(x_mul(m21, m33), x_mul(m31, m23));
+    const double minor_m11_m22 = x_sub(x_mul(m21, m32), x_mul(m31, m22));
+    const double det =
+        x_add(x_sub(x_mul(m11, minor_m12_m23), x_mul(m12, minor_m11_m23)), x_mul(m13, minor_m11_m22));
+    if (det == 0.0) return false;
+    out[0] = x_div(minor_m12_m23, det);
+    out[3] = x_div(x_sub(x_mul(m13, m32), x_mul(m33, m12)), det);
+    out[6] = x_div(x_sub(x_mul(m12, m23), x_mul(m22, m13)), det);
+    out[1] = x_div(-minor_m11_m23, det);
+    out[4] = x_div(x_sub(x_mul(m11, m33), x_mul(m31, m13)), det);
+    out[7] = x_div(x_sub(x_mul(m13, m21), x_mul(m23, m11)), det);
+    out[2] = x_div(minor_m11_m22, det);
+    out[5] = x_div(x_sub(x_mul(m12, m31), x_mul(m32, m11)), det);
+    out[8] = x_div(x_sub(x_mul(m11, m22), x_mul(m21, m12)), det);
+    return true;
+  } else if constexpr (N == 4) {
+    // do_inverse4: six-term cofactors a*b*c -/+ ..., evaluated left to right
+#define T3(s, a, b, c) (s x_mul(x_mul(a, b), c))
+#define COF(t0, t1, t2, t3, t4, t5) x_add(x_add(x_add(x_add(x_add(t0, t1), t2), t3), t4), t5)
+    const double c00 = COF(T3(+, m[5], m[10], m[15]), T3(-, m[5], m[11], m[14]), T3(-, m[9], m[6], m[15]),
+                           T3(+, m[9], m[7], m[14]), T3(+, m[13], m[6], m[11]), T3(-, m[13], m[7], m[10]));
+    const double c01 = COF(T3(+, -m[4], m[10], m[15]), T3(+, m[4], m[11], m[14]), T3(+, m[8], m[6], m[15]),
+                           T3(-, m[8], m[7], m[14]), T3(-, m[12], m[6], m[11]), T3(+, m[12], m[7], m[10]));
+    const double c02 = COF(T3(+, m[4], m[9], m[15]), T3(-, m[4], m[11], m[13]), T3(-, m[8], m[5], m[15]),
+                           T3(+, m[8], m[7], m[13]), T3(+, m[12], m[5], m[11]), T3(-, m[12], m[7], m[9]));
+    const double c03 = COF(T3(+, -m[4], m[9], m[14]), T3(+, m[4], m[10], m[13]), T3(+, m[8], m[5], m[14]),
+                           T3(-, m[8], m[6], m[13]), T3(-, m[12], m[5], m[10]), T3(+, m[12], m[6], m[9]));
+    const double det =
+        x_add(x_add(x_add(x_mul(m[0], c00), x_mul(m[1], c01)), x_mul(m[2], c02)), x_mul(m[3], c03));
+    if (det == 0.0) return false;
+    double inv[16];
+    inv[0] = c00;
+    inv[1] = COF(T3(+, -m[1], m[10], m[15]), T3(+, m[1], m[11], m[14]), T3(+, m[9], m[2], m[15]),
+                 T3(-, m[9], m[3], m[14]), T3(-, m[13], m[2], m[11]), T3(+, m[13], m[3], m[10]));
+    inv[2] = COF(T3(+, m[1], m[6], m[15]), T3(-, m[1], m[7], m[14]), T3(-, m[5], m[2], m[15]),
+                 T3(+, m[5], m[3], m[14]), T3(+, m[13], m[2], m[7]), T3(-, m[13], m[3], m[6]));
+    inv[3] = COF(T3(+, -m[1], m[6], m[11]), T3(+, m[1], m[7], m[10]), T3(+, m[5], m[2], m[11]),
+                 T3(-, m[5], m[3], m[10]), T3(-, m[9], m[2], m[7]), T3(+, m[9], m[3], m[6]));
+    inv[4] = c01;
+    inv[5] = COF(T3(+, m[0], m[10], m[15]), T3(-, m[0], m[11], m[14]), T3(-, m[8], m[2], m[15]),
+                 T3(+, m[8], m[3], m[14]), T3(+, m[12], m[2], m[11]), T3(-, m[12], m[3], m[10]));
+    inv[6] = COF(T3(+, -m[0], m[6], m[15]), T3(+, m[0], m[7], m[14]), T3(+, m[4], m[2], m[15]),
+                 T3(-, m[4], m[3], m[14]), T3(-, m[12], m[2], m[7]), T3(+, m[12], m[3], m[6]));
+    inv[7] = COF(T3(+, m[0], m[6], m[11]), T3(-, m[0], m[7], m[10]), T3(-, m[4], m[2], m[11]),
+                 T3(+, m[4], m[3], m[10]), T3(+, m[8], m[2], m[7]), T3(-, m[8], m[3], m[6]));
+    inv[8] = c02;
+    inv[9] = COF(T3(+, -m[0], m[9], m[15]), T3(+, m[0], m[11], m[13]), T3(+, m[8], m[1], m[15]),
+                 T3(-, m[8], m[3], m[13]), T3(-, m[12], m[1], m[11]), T3(+, m[12], m[3], m[9]));
+    inv[10] = COF(T3(+, m[0], m[5], m[15]), T3(-, m[0], m[7], m[13]), T3(-, m[4], m[1], m[15]),
+                  T3(+, m[4], m[3], m[13]), T3(+, m[12], m[1], m[7]), T3(-, m[12], m[3], m[5]));
+    inv[11] = COF(T3(+, -m[0], m[5], m[11]), T3(+, m[0], m[7], m[9]), T3(+, m[4], m[1], m[11]),
+                  T3(-, m[4], m[3], m[9]), T3(-, m[8], m[1], m[7]), T3(+, m[8], m[3], m[5]));
+    inv[12] = c03;
+    inv[13] = COF(T3(+, m[0], m[9], m[14]), T3(-, m[0], m[10], m[13]), T3(-, m[8], m[1], m[14]),
+                  T3(+, m[8], m[2], m[13]), T3(+, m[12], m[1], m[10]), T3(-, m[12], m[2], m[9]));
+    inv[14] = COF(T3(+, -m[0], m[5], m[14]), T3(+, m[0], m[6], m[13]), T3(+, m[4], m[1], m[14]),
+                  T3(-, m[4], m[2], m[13]), T3(-, m[12], m[1], m[6]), T3(+, m[12], m[2], m[5]));
+    inv[15] = COF(T3(+, m[0], m[5], m[10]), T3(-, m[0], m[6], m[9]), T3(-, m[4], m[1], m[10]),
+                  T3(+, m[4], m[2], m[9]), T3(+, m[8], m[1], m[6]), T3(-, m[8], m[2], m[5]));
+#undef T3
+#undef COF
+    const double inv_det = x_div(1.0, det);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) out[k] = x_mul(inv[k], inv_det);
+    return true;
+  } else {
+  // N >= 5: lu::try_invert_to
+  double a[N * N];
+#pragma unroll
+  for (int k = 0; k < N * N; ++k) {
+    a[k] = m[k];
+    out[k] = ((k % N) == (k / N)) ? 1.0 : 0.0;
+  }
+  for (int i = 0; i < N; ++i) {
+    int piv = i;
+    double the_max = fabs(a[i + i * N]);
+    for (int r = i + 1; r < N; ++r) {
+      const double v = fabs(a[r + i * N]);
+      if (v > the_max) {
+        the_max = v;
+        piv = r;
+      }
+    }
+    const double diag = a[piv + i * N];
+    if (diag == 0.0) return false;
+    if (piv != i) {
+      for (int j = 0; j < N; ++j) {
+        const double t = out[i + j * N];
+        out[i + j * N] = out[piv + j * N];
+        out[piv + j * N] = t;
+      }
+      for (int j = 0; j <= i; ++j) {  // columns ..i of the L part, and the coefficient column i
+        const double t = a[i + j * N];
+        a[i + j * N] = a[piv + j * N];
+        a[piv + j * N] = t;
+      }
+    }
+    const double inv_diag = x_div(1.0, diag);
+    for (int r = i + 1; r < N; ++r) a[r + i * N] = x_mul(a[r + i * N], inv_diag);
+    for (int k = i + 1; k < N; ++k) {
+      if (piv != i) {
+        const double t = a[i + k * N];
+        a[i + k * N] = a[piv + k * N];
+        a[piv + k * N] = t;
+      }
+      const double neg_pivot = -a[i + k * N];
+      for (int r = i + 1; r < N; ++r) a[r + k * N] = x_add(x_mul(neg_pivot, a[r + i * N]), a[r + k * N]);
+    }
+  }
+  for (int c = 0; c < N; ++c)
+    for (int i = 0; i + 1 < N; ++i) {
+      const double coeff = out[i + c * N];  // b[i] / 1.0
+      for (int r = i + 1; r < N; ++r) out[r + c * N] = x_add(x_mul(-coeff, a[r + i * N]), out[r + c * N]);
+    }
+  for (int c = 0; c < N; ++c)
+    for (int i = N - 1; i >= 0; --i) {
+      const double diag = a[i + i * N];
+      if (diag == 0.0) return false;
+      const double coeff = x_div(out[i + c * N], diag);
+      out[i + c * N] = coeff;
+      for (int r = 0; r < i; ++r) out[r + c * N] = x_add(x_mul(-coeff, a[r + i * N]), out[r + c * N]);
+    }
+  return true;
+  }
 }
-cudaError_t multi_resident_launch(const BatchDev&, const LaunchGeom&, cudaStream_t) { return cudaErrorNotSupported; }
+
+// compute_row in the reference's order.  c[], up[] -> k[] = dC/dt of this cell.
+template <int N>
+__device__ void exact_row(const SpeciesConst* sc, double fe, double ue, double dz, const double* c, const double* up,
+                          double* k) {
+  double sum_kc = 0.0;
+#pragma unroll
+  for (int s = 0; s < N; ++s) sum_kc = x_add(sum_kc, x_mul(sc[s].K, c[s]));
+  const double denom = x_add(1.0, sum_kc);
+  const double denom2 = x_mul(denom, denom);
+  double mat[N * N], inv[N * N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double nb = sc[i].nbar, Ki = sc[i].K;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      double J;
+      if (i == j) {
+        const double num = x_mul(x_mul(nb, Ki), x_sub(denom, x_mul(Ki, c[i])));
+        J = x_add(sc[i].lambda, x_div(num, denom2));
+      } else {
+        const double num = x_mul(x_mul(x_mul(-nb, Ki), sc[j].K), c[i]);
+        J = x_div(num, denom2);
+      }
+      mat[i + j * N] = x_add((i == j) ? 1.0 : 0.0, x_mul(fe, J));
+    }
+  }
+  if (!exact_try_inverse<N>(mat, inv)) {  // identity fallback, langmuir_multi.rs:790-796
+#pragma unroll
+    for (int q = 0; q < N * N; ++q) inv[q] = ((q % N) == (q / N)) ? 1.0 : 0.0;
+  }
+  double grad[N], dv[N];
+#pragma unroll
+  for (int s = 0; s < N; ++s) grad[s] = x_div(x_sub(c[s], up[s]), dz);
+#pragma unroll
+  for (int i = 0; i < N; ++i) dv[i] = x_mul(inv[i], grad[0]);
+#pragma unroll
+  for (int j = 1; j < N; ++j)
+#pragma unroll
+    for (int i = 0; i < N; ++i) dv[i] = x_add(x_mul(inv[i + j * N], grad[j]), dv[i]);
+#pragma unroll
+  for (int s = 0; s < N; ++s) k[s] = x_mul(-ue, dv[s]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FAST: A = I + fe*M = diag(alpha) - p q^T built in registers, LU with partial pivoting applied to
+// rhs = (-ue/dz)*(c - up), back substitution.  k = A^-1 rhs.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long abs_bits(double v) {
+  return (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull;
+}
+
+// One elimination step with a compile-time pivot column I (template recursion instead of a loop:
+// every register index is a constant, so the matrix never falls back to local memory).
+template <int N, int I>
+__device__ __forceinline__ void lu_step(double (&a)[N][N], double (&b)[N], bool& singular) {
+  if constexpr (I + 1 < N) {
+    // Partial pivoting.  Cheap test first (integer pipe): can any row below hold a larger |entry|?
+    // High words only, '>=' so that ties in the high word are never missed.  The matrices are
+    // close to diagonally dominant, so the swap path below is almost never entered.
+    unsigned below = 0u;
+#pragma unroll
+    for (int r = I + 1; r < N; ++r) below = max(below, abs_hi(a[r][I]));
+    if (__any_sync(0xffffffffu, below >= abs_hi(a[I][I]))) {
+      // Exact path: compare-and-swap row I against every row below.  Afterwards
+      // |a[I][I]| = max_r |a[r][I]|: a valid partial pivot.
+#pragma unroll
+      for (int r = I + 1; r < N; ++r) {
+        const bool sw = abs_bits(a[r][I]) > abs_bits(a[I][I]);
+#pragma unroll
+        for (int q = I; q < N; ++q) {
+          const double t = a[I][q];
+          a[I][q] = sw ? a[r][q] : t;
+          a[r][q] = sw ? t : a[r][q];
+        }
+        const double t = b[I];
+        b[I] = sw ? b[r] : t;
+        b[r] = sw ? t : b[r];
+      }
+    }
+  }
+  singular |= (a[I][I] == 0.0);
+  const double rp = fast_rcp(a[I][I]);
+  a[I][I] = rp;  // keep the reciprocal for the back substitution
+#pragma unroll
+  for (int r = I + 1; r < N; ++r) {
+    const double l = a[r][I] * rp;
+#pragma unroll
+    for (int q = I + 1; q < N; ++q) a[r][q] = fma(-l, a[I][q], a[r][q]);
+    b[r] = fma(-l, b[I], b[r]);
+  }
+  if constexpr (I + 1 < N) lu_step<N, I + 1>(a, b, singular);
+}
+
+template <int N, int I>
+__device__ __forceinline__ void back_step(const double (&a)[N][N], const double (&b)[N], double* k) {
+  double s = b[I];
+#pragma unroll
+  for (int q = I + 1; q < N; ++q) s = fma(-a[I][q], k[q], s);
+  k[I] = s * a[I][I];
+  if constexpr (I > 0) back_step<N, I - 1>(a, b, k);
+}
+
+template <int N>
+__device__ __forceinline__ void fast_row(const SpeciesConst* sc, double fe, double cg, const double* c,
+                                         const double* up, double* k) {
+  (void)fe;
+  double S = 0.0;
+#pragma unroll
+  for (int s = 0; s < N; ++s) S = fma(sc[s].K, c[s], S);
+  const double D = 1.0 + S;
+  const double rD2 = fast_rcp(D * D);
+  const double DrD2 = D * rD2;
+  double a[N][N], b[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double p = sc[i].feNK * c[i] * rD2;  // fe * nbar_i K_i c_i / D^2
+#pragma unroll
+    for (int j = 0; j < N; ++j) a[i][j] = -p * sc[j].K;
+    a[i][i] = fma(sc[i].feNK, DrD2, sc[i].a0) + a[i][i];  // 1 + fe*(lambda_i + nbar_i K_i (D - K_i c_i)/D^2)
+    b[i] = (c[i] - up[i]) * cg;
+  }
+  bool singular = false;
+  lu_step<N, 0>(a, b, singular);
+  back_step<N, N - 1>(a, b, k);
+  if (singular) {  // exact zero pivot: the reference falls back to the identity (A^-1 := I)
+#pragma unroll
+    for (int s = 0; s < N; ++s) k[s] = (c[s] - up[s]) * cg;
+  }
+}
+
+constexpr int multi_max_threads(int N) { return N <= 2 ? 512 : 256; }
+
+template <int N, int METHOD, bool EXACT>
+__global__ void __launch_bounds__(multi_max_threads(N), 1) k_multi_resident(const BatchDev b) {
+  constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
+  extern __shared__ double smem[];
+  const uint32_t nz = b.nz;
+  const uint32_t col = blockIdx.x;
+  const int T = blockDim.x;
+  const int tid = threadIdx.x;
+  const size_t plane = (size_t)N * nz;  // doubles per state array
+  double* Y = smem;
+  double* ACC = Y + plane;
+  double* U0 = ACC + plane;
+  double* U1 = U0 + plane;
+  double* inlet = U1 + plane;                              // [3][N] current step's inlet values
+  double* summ = inlet + 3 * N;                            // [N][5]: area, moment, max, tmax, v_prev
+  SpeciesConst* sc = (SpeciesConst*)(summ + 5 * N);        // [N]
+  __shared__ const double* tabs[N];
+
+  const chrom_multi_col cp = b.mcols[col];
+  const double fe = cp.fe, ue = cp.ue, dz = cp.dz;
+  const double cg = -ue / dz;  // FAST only
+  if (tid < N) {
+    const chrom_species sp = b.species[cp.species_off + tid];
+    SpeciesConst s;
+    s.lambda = sp.lambda;
+    s.K = sp.langmuir_k;
+    s.nbar = EXACT ? x_mul(cp.stationary_fraction, (double)sp.port_number)
+                   : cp.stationary_fraction * (double)sp.port_number;
+    s.a0 = 1.0 + fe * sp.lambda;
+    s.feNK = fe * (s.nbar * sp.langmuir_k);
+    sc[tid] = s;
+    tabs[tid] = b.tables + (size_t)sp.inj_table * b.steps * ST;
+  }
+  for (size_t i = tid; i < plane; i += T) {
+    Y[i] = b.y0 ? b.y0[(size_t)col * plane + i] : 0.0;
+    ACC[i] = 0.0;
+  }
+  __syncthreads();
+
+  const double dt = b.dt, h2 = b.half_dt, h6 = b.sixth_dt;
+  const uint32_t steps = b.steps;
+  const int cpt = (int)((nz + T - 1) / T);  // cells per thread
+  const bool out_thread = ((int)((nz - 1) % T) == tid);
+
+  auto axpy = [](double y, double k, double h) { return EXACT ? x_add(y, x_mul(k, h)) : fma(k, h, y); };
+
+  // initial samples
+  if (b.outlet && tid < N) b.outlet[((size_t)col * N + tid) * b.n_out] = Y[(size_t)tid * nz + nz - 1];
+  if (b.snapshots)
+    for (size_t i = tid; i < plane; i += T) b.snapshots[(size_t)col * b.n_snap * plane + i] = Y[i];
+  if (tid < N) {
+    const double v0 = Y[(size_t)tid * nz + nz - 1];
+    summ[tid * 5 + 0] = 0.0;
+    summ[tid * 5 + 1] = 0.0;
+    summ[tid * 5 + 2] = v0;
+    summ[tid * 5 + 3] = 0.0;
+    summ[tid * 5 + 4] = v0;
+  }
+  uint32_t out_count = b.outlet_stride, snap_count = b.snapshot_stride, out_slot = 1, snap_slot = 1;
+  bool done = false;
+
+  // One stage: K = f(SRC, inlet row `irow`), then the stage algebra selected by `stage`.
+  auto run_stage = [&](const double* SRC, double* DST, int irow, int stage) -> bool {
+    bool bad = false;
+    for (int ci = 0; ci < cpt; ++ci) {
+      const uint32_t cell = (uint32_t)tid + (uint32_t)ci * T;
+      const bool live = cell < nz;
+      const uint32_t cc = live ? cell : nz - 1;  // idle lanes recompute the last cell, never store
+      double c[N], up[N], k[N];
+#pragma unroll
+      for (int s = 0; s < N; ++s) {
+        c[s] = SRC[(size_t)s * nz + cc];
+        up[s] = (cc > 0) ? SRC[(size_t)s * nz + cc - 1] : inlet[irow * N + s];
+      }
+      if (EXACT) exact_row<N>(sc, fe, ue, dz, c, up, k);
+      else fast_row<N>(sc, fe, cg, c, up, k);
+      if (!live) continue;
+#pragma unroll
+      for (int s = 0; s < N; ++s) {
+        const size_t idx = (size_t)s * nz + cc;
+        if (METHOD == CHROM_EULER) {
+          const double yn = axpy(Y[idx], k[s], dt);
+          Y[idx] = yn;  // Euler reads SRC = U0 (copy of Y), so Y can be overwritten
+          DST[idx] = yn;
+          bad |= hi_nonfinite(abs_hi(yn));
+        } else if (stage == 1) {
+          ACC[idx] = k[s];
+          DST[idx] = axpy(Y[idx], k[s], h2);
+        } else if (stage == 2) {
+          ACC[idx] = axpy(ACC[idx], k[s], 2.0);
+          DST[idx] = axpy(Y[idx], k[s], h2);
+        } else if (stage == 3) {
+          ACC[idx] = axpy(ACC[idx], k[s], 2.0);
+          DST[idx] = axpy(Y[idx], k[s], dt);
+        } else {
+          const double w = EXACT ? x_add(ACC[idx], k[s]) : ACC[idx] + k[s];
+          const double yn = axpy(Y[idx], w, h6);
+          Y[idx] = yn;
+          bad |= hi_nonfinite(abs_hi(yn));
+        }
+      }
+    }
+    return bad;
+  };
+
+  if (METHOD == CHROM_EULER) {
+    for (size_t i = tid; i < plane; i += T) U0[i] = Y[i];
+  }
+
+  for (uint32_t step = 0; step < steps; ++step) {
+    if (tid < N * ST) {  // inlet values of this step: [stage row][species]
+      const int s = tid % N, r = tid / N;
+      inlet[r * N + s] = tabs[s][(size_t)step * ST + r];
+    }
+    __syncthreads();
+    bool bad;
+    if (METHOD == CHROM_RK4) {
+      run_stage(Y, U0, 0, 1);
+      __syncthreads();
+      run_stage(U0, U1, 1, 2);
+      __syncthreads();
+      run_stage(U1, U0, 1, 3);
+      __syncthreads();
+      bad = run_stage(U0, nullptr, 2, 4);
+    } else {
+      // ping-pong: even steps read U0 / write U1, odd steps the reverse; Y always holds the new state
+      bad = (step & 1u) ? run_stage(U1, U0, 0, 0) : run_stage(U0, U1, 0, 0);
+    }
+    const int any_bad = __syncthreads_or(bad);
+
+    // ---- samples ----------------------------------------------------------------------------
+    if (tid < N) {
+      const double v = Y[(size_t)tid * nz + nz - 1];
+      if (b.outlet && --out_count == 0) {
+        out_count = b.outlet_stride;
+        b.outlet[((size_t)col * N + tid) * b.n_out + out_slot] = v;
+        ++out_slot;
+      }
+      if (b.summary) {
+        const double t0 = (double)step * dt, t1 = ((double)step + 1.0) * dt;
+        const double w = 0.5 * (t1 - t0);
+        double* sm = summ + tid * 5;
+        sm[0] = fma(w, sm[4] + v, sm[0]);
+        sm[1] = fma(w, fma(t0, sm[4], t1 * v), sm[1]);
+        if (v > sm[2]) {
+          sm[2] = v;
+          sm[3] = t1;
+        }
+        sm[4] = v;
+      }
+    }
+    if (b.snapshots && --snap_count == 0) {
+      snap_count = b.snapshot_stride;
+      double* dst = b.snapshots + ((size_t)col * b.n_snap + snap_slot) * plane;
+      for (size_t i = tid; i < plane; i += T) dst[i] = Y[i];
+      ++snap_slot;
+    }
+    if (any_bad && !done) {  // validate_state: NaN anywhere wins over Inf (solver/mod.rs:519-548)
+      bool has_nan = false;
+      for (size_t i = tid; i < plane; i += T) has_nan |= (Y[i] != Y[i]);
+      const int any_nan = __syncthreads_or(has_nan);
+      if (tid == 0 && b.status) b.status[col] = any_nan ? (long long)(step + 1) : -(long long)(step + 1);
+      done = true;
+    }
+  }
+  (void)out_thread;
+  __syncthreads();
+  if (b.final_state)
+    for (size_t i = tid; i < plane; i += T) b.final_state[(size_t)col * plane + i] = Y[i];
+  if (b.summary && tid < N) {
+    double* s = b.summary + ((size_t)col * N + tid) * 4;
+    const double* sm = summ + tid * 5;
+    s[0] = sm[0];
+    s[1] = (sm[0] != 0.0) ? sm[1] / sm[0] : 0.0;
+    s[2] = sm[2];
+    s[3] = sm[3];
+  }
+}
+
+typedef void (*mkern_t)(const BatchDev);
+
+template <int N>
+mkern_t pick_n(int method, int arith) {
+  if (method == CHROM_RK4)
+    return arith == CHROM_ARITH_EXACT ? k_multi_resident<N, CHROM_RK4, true> : k_multi_resident<N, CHROM_RK4, false>;
+  return arith == CHROM_ARITH_EXACT ? k_multi_resident<N, CHROM_EULER, true> : k_multi_resident<N, CHROM_EULER, false>;
+}
+
+mkern_t lookup_multi(int n, int method, int arith) {
+  switch (n) {
+    case 1: return pick_n<1>(method, arith);
+    case 2: return pick_n<2>(method, arith);
+    case 3: return pick_n<3>(method, arith);
+    case 4: return pick_n<4>(method, arith);
+    case 5: return pick_n<5>(method, arith);
+    case 6: return pick_n<6>(method, arith);
+    case 7: return pick_n<7>(method, arith);
+    case 8: return pick_n<8>(method, arith);
+  }
+  return nullptr;
+}
+
+size_t multi_smem_bytes(int n, uint32_t nz) {
+  return ((size_t)4 * n * nz + 3 * n + 5 * n) * sizeof(double) + (size_t)n * sizeof(SpeciesConst);
+}
+
+}  // namespace
+
+bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why) {
+  (void)sm_count;
+  const int n = (int)b.n_species;
+  if (n < 1 || n > 8) {
+    if (why) *why = "n_species outside 1..8 (per-thread register LU); the warp-per-cell path is not built yet";
+    return false;
+  }
+  const size_t smem = multi_smem_bytes(n, b.nz);
+  if (smem > 227u * 1024u) {
+    if (why) *why = "nz * n_species exceeds the shared-memory-resident capacity (4*n*nz doubles <= 227 KB)";
+    return false;
+  }
+  const int tmax = multi_max_threads(n);
+  int T = (int)std::min<uint32_t>((b.nz + 31u) / 32u * 32u, (uint32_t)tmax);
+  // balance: fewest threads that keep the same number of cells per thread
+  const int cpt = (int)((b.nz + T - 1) / T);
+  T = (int)(((b.nz + cpt - 1) / cpt + 31u) / 32u * 32u);
+  g->kind = 4;
+  g->M = cpt;
+  g->L = T;
+  g->cpw = 1;
+  g->warps_per_col = T / 32;
+  g->block = dim3(T);
+  g->grid = dim3(b.n_cols);
+  g->smem = smem;
+  char buf[200];
+  snprintf(buf, sizeof buf, "multi_resident<n=%d,%s,%s> threads/col=%d cells/thread=%d smem=%zuB grid=%u", n,
+           b.method == CHROM_RK4 ? "RK4" : "Euler", b.arith == CHROM_ARITH_EXACT ? "exact" : "fast", T, cpt, smem,
+           b.n_cols);
+  g->name = buf;
+  return true;
+}
+
+cudaError_t multi_resident_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s) {
+  mkern_t k = lookup_multi((int)b.n_species, b.method, b.arith);
+  if (!k) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+  if (e != cudaSuccess) return e;
+  k<<<g.grid, g.block, g.smem, s>>>(b);
+  return cudaGetLastError();
+}
+
 }  // namespace chrom
