@@ -238,8 +238,11 @@ int32_t build_shard(chrom_cuda_plan* plan, Shard& sh, const chrom_single_col* sc
     ok = single_resident_choose(b, d.sm_count, &sh.g, &why);
     if (!ok) ok = single_stream_choose(b, d.sm_count, &sh.g, &why);
     if (ok && sh.g.kind == 3) {
+      if ((want & CHROM_WANT_SUMMARY) && !(sh.outlet.p && cfg.outlet_stride == 1))
+        return fail(ctx, CHROM_ERR_UNSUPPORTED,
+                    "summary on the streaming path (nz > 8192) needs the outlet requested with outlet_stride == 1");
       CUDA_TRY(ctx, sh.ping.alloc(sh.n_cols * state_len));
-      CUDA_TRY(ctx, sh.pong.alloc(sh.n_cols * state_len));
+      CUDA_TRY(ctx, sh.pong.alloc(sh.n_cols * (state_len + 1)));  // + one status code per column
       b.ping = sh.ping.p;
       b.pong = sh.pong.p;
     }

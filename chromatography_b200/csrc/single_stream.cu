@@ -1,9 +1,283 @@
-// single_stream.cu — placeholder until the streaming kernel lands.
+// single_stream.cu — LangmuirSingle columns too long for the register-resident path (nz > 8192,
+// e.g. the nz = 2^22 spatial-convergence column of BASELINE config 4): the state streams through
+// HBM/L2 once per time step, all four RK4 stages fused in one pass.
+//
+// Replaces per launch ONE iteration of the time loop (rk4.rs:266-332 / euler.rs:227-269) with
+// LangmuirSingle::compute_physics (langmuir_single.rs:445-516) evaluated 4 (or 1) times in registers.
+//
+// Tiling: a warp owns 32*M consecutive cells, M per lane (same register scheme as
+// single_resident.cu: one shuffle per lane per stage).  RK4 needs the stage values of the four cells
+// upstream of a tile; instead of exchanging them the tile simply starts 4 cells early and discards
+// its first 4 results (they are recomputed, correctly, by the previous tile): 1.6 % redundant work
+// at M = 8, no inter-CTA communication.  Tile 0 starts at the inlet and keeps everything.
+// Algorithmic HBM traffic: 16 B per cell-step (read y_n, write y_n+1); both ping-pong buffers of
+// the 2^22 column (67 MB) fit the 126 MB L2.
+#include <cstdio>
+
+#include "arith.cuh"
 #include "kernels.h"
+#include "single_rhs.cuh"
+
 namespace chrom {
-bool single_stream_choose(const BatchDev&, int, LaunchGeom*, std::string* why) {
-  if (why) *why += "; streaming path not built yet";
-  return false;
+namespace {
+
+constexpr int kM = 8;           // cells per lane
+constexpr int kTile = 32 * kM;  // cells per warp tile
+constexpr int kWarps = 4;       // warps per CTA
+
+// status word while streaming: 0 = clean, else (step << 1) | has_nan; atomicMax keeps NaN over Inf
+// within a step, later steps never overwrite (solver/mod.rs:519-548: NaN wins, first step wins).
+template <int METHOD, bool EXACT>
+__global__ void __launch_bounds__(kWarps * 32)
+    k_single_stream_step(const BatchDev b, const double* __restrict__ src, double* __restrict__ dst, uint32_t step,
+                         unsigned long long* __restrict__ code, int out_slot, int tiles_per_col) {
+  constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
+  constexpr int H = (METHOD == CHROM_RK4) ? 4 : 0;  // RK4 stage values reach 4 cells upstream
+  constexpr int V = kTile - H;  // cells a non-first tile contributes
+  using Q = Coef<EXACT>;
+  const int lane = threadIdx.x & 31;
+  const int tile = (int)(blockIdx.x * kWarps + (threadIdx.x >> 5));
+  const uint32_t col = blockIdx.y;
+  if (tile >= tiles_per_col) return;
+  const uint32_t nz = b.nz;
+  // Tile 0 covers [0, kTile); tile t >= 1 starts H cells early: kTile + (t-1)*V - H = t*V since
+  // V = kTile - H.  Written without a select on purpose: `(tile == 0) ? 0 : 64-bit expr` made
+  // ptxas 12.9 emit CS2R R, SRZ + predicated IMAD.WIDE + an under-stalled consumer (tile 0 read a
+  // stale register in the Euler/fast variant; found by the parity tests).
+  const long long base = (long long)tile * V;
+  const long long cell0 = base + (long long)lane * kM;
+  const int first_valid = (tile == 0) ? 0 : H;  // tile-local index of the first cell this tile stores
+
+  const chrom_single_col cp = b.scols[col];
+  Q q;
+  q.init(cp);
+  const double* __restrict__ tab = b.tables + ((size_t)cp.inj_table * b.steps + step) * ST;
+  const double cin0 = tab[0];
+  const double cin1 = (ST == 3) ? tab[1] : 0.0;
+  const double cin2 = (ST == 3) ? tab[2] : 0.0;
+  const double dt = b.dt, h2 = b.half_dt, h6 = b.sixth_dt;
+
+  const double* __restrict__ s = src + (size_t)col * nz;
+  double* __restrict__ d = dst + (size_t)col * nz;
+  double y[kM], u[kM], acc[kM];
+  const bool vec = ((nz & 1u) == 0u) && (cell0 + kM <= (long long)nz);
+  if (vec) {
+    const double2* sv = reinterpret_cast<const double2*>(s + cell0);
+#pragma unroll
+    for (int j = 0; j < kM / 2; ++j) {
+      const double2 v = sv[j];
+      y[2 * j] = v.x;
+      y[2 * j + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kM; ++j) y[j] = (cell0 + j < (long long)nz) ? s[cell0 + j] : 0.0;
+  }
+  const bool inlet_lane = (tile == 0) && (lane == 0);
+
+  auto exchange = [&](double last, double inlet) -> double {
+    const double up = __shfl_up_sync(0xffffffffu, last, 1);
+    return inlet_lane ? inlet : up;  // lane 0 of a later tile gets its own value back: halo, discarded
+  };
+
+  if (METHOD == CHROM_RK4) {
+    double up = exchange(y[kM - 1], cin0);
+#pragma unroll
+    for (int j = kM - 1; j >= 0; --j) {
+      const double k = q.rhs(y[j], j > 0 ? y[j - 1] : up);
+      acc[j] = k;
+      u[j] = Q::axpy(y[j], k, h2);
+    }
+    up = exchange(u[kM - 1], cin1);
+#pragma unroll
+    for (int j = kM - 1; j >= 0; --j) {
+      const double k = q.rhs(u[j], j > 0 ? u[j - 1] : up);
+      acc[j] = Q::axpy(acc[j], k, 2.0);
+      u[j] = Q::axpy(y[j], k, h2);
+    }
+    up = exchange(u[kM - 1], cin1);
+#pragma unroll
+    for (int j = kM - 1; j >= 0; --j) {
+      const double k = q.rhs(u[j], j > 0 ? u[j - 1] : up);
+      acc[j] = Q::axpy(acc[j], k, 2.0);
+      u[j] = Q::axpy(y[j], k, dt);
+    }
+    up = exchange(u[kM - 1], cin2);
+#pragma unroll
+    for (int j = kM - 1; j >= 0; --j) {
+      const double k = q.rhs(u[j], j > 0 ? u[j - 1] : up);
+      y[j] = Q::axpy(y[j], Q::add(acc[j], k), h6);
+    }
+  } else {
+    // Euler: the upstream neighbour of the tile's first cell is an input, read it directly
+    double up = exchange(y[kM - 1], cin0);
+    if (lane == 0 && tile > 0) up = s[cell0 - 1];
+#pragma unroll
+    for (int j = kM - 1; j >= 0; --j) {
+      const double k = q.rhs(y[j], j > 0 ? y[j - 1] : up);
+      y[j] = Q::axpy(y[j], k, dt);
+    }
+  }
+
+  // ---- store the valid cells, outlet sample, non-finite scan ---------------------------------------
+  const int local0 = lane * kM;  // tile-local index of this lane's first cell
+  bool bad = false, has_nan = false;
+  if (vec && local0 >= first_valid) {
+    double2* dv = reinterpret_cast<double2*>(d + cell0);
+#pragma unroll
+    for (int j = 0; j < kM / 2; ++j) dv[j] = make_double2(y[2 * j], y[2 * j + 1]);
+#pragma unroll
+    for (int j = 0; j < kM; ++j) {
+      bad |= hi_nonfinite(abs_hi(y[j]));
+      has_nan |= (y[j] != y[j]);
+    }
+    if (cell0 + kM == (long long)nz && out_slot >= 0) b.outlet[(size_t)col * b.n_out + out_slot] = y[kM - 1];
+  } else {
+#pragma unroll
+    for (int j = 0; j < kM; ++j) {
+      const long long cell = cell0 + j;
+      if (local0 + j >= first_valid && cell < (long long)nz) {
+        d[cell] = y[j];
+        bad |= hi_nonfinite(abs_hi(y[j]));
+        has_nan |= (y[j] != y[j]);
+        if (cell == (long long)nz - 1 && out_slot >= 0) b.outlet[(size_t)col * b.n_out + out_slot] = y[j];
+      }
+    }
+  }
+  if (__any_sync(0xffffffffu, bad)) {
+    const bool any_nan = __any_sync(0xffffffffu, has_nan);
+    if (lane == 0) {
+      const unsigned long long prev = code[col];  // nonzero from an EARLIER step: that step stays the answer
+      if (prev == 0ull || (prev >> 1) == (unsigned long long)(step + 1))
+        atomicMax(&code[col], ((unsigned long long)(step + 1) << 1) | (any_nan ? 1ull : 0ull));
+    }
+  }
 }
-cudaError_t single_stream_launch(const BatchDev&, const LaunchGeom&, cudaStream_t) { return cudaErrorNotSupported; }
+
+// After the last step: status codes -> the ABI's signed convention, summaries from the outlet series.
+__global__ void k_stream_finalize(const BatchDev b, const unsigned long long* __restrict__ code,
+                                  const double* __restrict__ full_outlet /* [n_cols][steps+1] or null */) {
+  const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= b.n_cols) return;
+  if (b.status) {
+    const unsigned long long c = code[col];
+    const long long s = (long long)(c >> 1);
+    b.status[col] = (c == 0ull) ? 0ll : ((c & 1ull) ? s : -s);
+  }
+  if (b.summary && full_outlet) {
+    const double* o = full_outlet + (size_t)col * (b.steps + 1);
+    double area = 0.0, mom = 0.0, vmax = o[0], tmax = 0.0, vp = o[0];
+    for (uint32_t st = 0; st < b.steps; ++st) {
+      const double v = o[st + 1];
+      const double t0 = (double)st * b.dt, t1 = ((double)st + 1.0) * b.dt;
+      const double w = 0.5 * (t1 - t0);
+      area = fma(w, vp + v, area);
+      mom = fma(w, fma(t0, vp, t1 * v), mom);
+      if (v > vmax) {
+        vmax = v;
+        tmax = t1;
+      }
+      vp = v;
+    }
+    double* sm = b.summary + (size_t)col * 4;
+    sm[0] = area;
+    sm[1] = (area != 0.0) ? mom / area : 0.0;
+    sm[2] = vmax;
+    sm[3] = tmax;
+  }
+}
+
+__global__ void k_stream_init(const BatchDev b, double* __restrict__ ping, unsigned long long* __restrict__ code) {
+  const size_t n = (size_t)b.n_cols * b.nz;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) ping[i] = b.y0 ? b.y0[i] : 0.0;
+  if (blockIdx.x == 0)
+    for (uint32_t c = threadIdx.x; c < b.n_cols; c += blockDim.x) code[c] = 0ull;
+}
+
+typedef void (*skern_t)(const BatchDev, const double*, double*, uint32_t, unsigned long long*, int, int);
+
+skern_t pick_stream(int method, int arith) {
+  if (method == CHROM_RK4)
+    return arith == CHROM_ARITH_EXACT ? k_single_stream_step<CHROM_RK4, true> : k_single_stream_step<CHROM_RK4, false>;
+  return arith == CHROM_ARITH_EXACT ? k_single_stream_step<CHROM_EULER, true>
+                                    : k_single_stream_step<CHROM_EULER, false>;
+}
+
+}  // namespace
+
+bool single_stream_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why) {
+  (void)sm_count;
+  (void)why;
+  const int H = b.method == CHROM_RK4 ? 4 : 0;
+  const int V = kTile - H;
+  const long long rest = (long long)b.nz - kTile;
+  const int tiles = 1 + (rest > 0 ? (int)((rest + V - 1) / V) : 0);
+  g->kind = 3;
+  g->M = kM;
+  g->L = 32;
+  g->cpw = 0;
+  g->warps_per_col = tiles;
+  g->block = dim3(kWarps * 32);
+  g->grid = dim3((tiles + kWarps - 1) / kWarps, b.n_cols);
+  g->smem = 0;
+  g->launches_per_execute = (uint64_t)b.steps + 2;
+  char buf[200];
+  snprintf(buf, sizeof buf, "single_stream<M=%d,%s,%s> tiles/col=%d halo=%d grid=(%u,%u) block=%d, 1 launch per step", kM,
+           b.method == CHROM_RK4 ? "RK4" : "Euler", b.arith == CHROM_ARITH_EXACT ? "exact" : "fast", tiles, H, g->grid.x,
+           g->grid.y, kWarps * 32);
+  g->name = buf;
+  return true;
+}
+
+// b.ping: [n_cols][nz]; b.pong: [n_cols][nz] followed by n_cols 64-bit status codes (the caller
+// allocates n_cols*(nz+1) doubles).  Summaries need the full-rate outlet: b.outlet with stride 1.
+
+cudaError_t single_stream_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s) {
+  skern_t k = pick_stream(b.method, b.arith);
+  unsigned long long* code = reinterpret_cast<unsigned long long*>(b.pong + (size_t)b.n_cols * b.nz);
+  const size_t plane = (size_t)b.n_cols * b.nz;
+  k_stream_init<<<296, 256, 0, s>>>(b, b.ping, code);
+  double* src = b.ping;
+  double* dst = b.pong;
+  if (b.outlet) {  // slot 0: the outlet of the initial state
+    for (uint32_t c = 0; c < b.n_cols; ++c) {
+      cudaError_t e = cudaMemcpyAsync(b.outlet + (size_t)c * b.n_out, src + (size_t)c * b.nz + b.nz - 1, sizeof(double),
+                                      cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  auto snapshot = [&](const double* state, uint32_t slot) -> cudaError_t {
+    for (uint32_t c = 0; c < b.n_cols; ++c) {
+      cudaError_t e = cudaMemcpyAsync(b.snapshots + ((size_t)c * b.n_snap + slot) * b.nz, state + (size_t)c * b.nz,
+                                      (size_t)b.nz * sizeof(double), cudaMemcpyDeviceToDevice, s);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  };
+  if (b.snapshots) {
+    cudaError_t e = snapshot(src, 0);
+    if (e != cudaSuccess) return e;
+  }
+  for (uint32_t step = 0; step < b.steps; ++step) {
+    int out_slot = -1;
+    if (b.outlet && b.outlet_stride && ((step + 1) % b.outlet_stride == 0)) out_slot = (int)((step + 1) / b.outlet_stride);
+    k<<<g.grid, g.block, 0, s>>>(b, src, dst, step, code, out_slot, g.warps_per_col);
+    if (b.snapshots && b.snapshot_stride && ((step + 1) % b.snapshot_stride == 0)) {
+      cudaError_t e = snapshot(dst, (step + 1) / b.snapshot_stride);
+      if (e != cudaSuccess) return e;
+    }
+    double* t = src;
+    src = dst;
+    dst = t;
+  }
+  if (b.final_state) {
+    cudaError_t e = cudaMemcpyAsync(b.final_state, src, plane * sizeof(double), cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return e;
+  }
+  const double* full = (b.outlet && b.outlet_stride == 1) ? b.outlet : nullptr;
+  k_stream_finalize<<<(b.n_cols + 127) / 128, 128, 0, s>>>(b, code, full);
+  return cudaGetLastError();
+}
+
 }  // namespace chrom
