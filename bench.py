@@ -197,6 +197,55 @@ class ClockSampler:
                 "power_w_max": hi, "samples": len(sm)}
 
 
+# ---- one process per GPU: the only cross-rank traffic is the barrier and two scalar reductions ----------
+class Ranks:
+    """torch.distributed plumbing of the bench (no data-path collective: columns are independent).
+    backend "nccl" on the GPU box, "gloo" in the CPU tests (tests/test_dist_gloo.py)."""
+
+    def __init__(self, backend: str, local_rank: int = 0):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.distributed = self.world > 1
+        self.cuda = backend == "nccl"
+        if self.distributed:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            if self.cuda:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            else:
+                dist.init_process_group(backend)
+
+    def barrier(self):
+        if self.distributed:
+            self.dist.barrier()
+        if self.cuda:
+            self.torch.cuda.synchronize()
+
+    def _reduce(self, x: float, op) -> float:
+        if not self.distributed:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda" if self.cuda else "cpu")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x: float) -> float:
+        return self._reduce(x, self.dist.ReduceOp.MAX)
+
+    def sum(self, x: float) -> float:
+        return self._reduce(x, self.dist.ReduceOp.SUM)
+
+    def close(self):
+        if self.distributed:
+            self.dist.destroy_process_group()
+
+
+def aggregate_value(ranks: "Ranks", units_this_rank: float, device_ms_this_rank: float) -> float:
+    """Whole-job throughput: units all ranks processed / max-over-ranks of the device time."""
+    return ranks.sum(units_this_rank) / (ranks.max(device_ms_this_rank) * 1e-3)
+
+
 # ---- GPU arm ------------------------------------------------------------------------------------------
 def pinned_array(lib, shape, dtype=np.float64):
     n = int(np.prod(shape))
@@ -256,33 +305,11 @@ def main():
 
     W_ = max(args.warmup, 3)  # timing rule: at least 3 warm-up steps
     import torch
-    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: chromatography_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    distributed = world > 1
-    if distributed:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if distributed:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if not distributed:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x: float) -> float:
-        if not distributed:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    ranks = Ranks("nccl", local_rank)
+    distributed, barrier, max_over_ranks, sum_over_ranks = ranks.distributed, ranks.barrier, ranks.max, ranks.sum
 
     import chromatography_b200 as cb
     from chromatography_b200 import _ffi
@@ -315,8 +342,7 @@ def main():
     wall_ms = (time.perf_counter() - wall0) * 1e3
     clocks = sampler.stop() if sampler else None
     t_dev_ms = max_over_ranks(sum(kernel_ms))
-    total_units = sum_over_ranks(units_rank) * args.steps
-    value = total_units / (t_dev_ms * 1e-3)
+    value = aggregate_value(ranks, units_rank * args.steps, sum(kernel_ms))
     st = plan.download().status
     n_bad = int(np.count_nonzero(st))
     plan.close()
@@ -393,8 +419,7 @@ def main():
         }
         print(json.dumps(line), flush=True)
     ctx.close()
-    if distributed:
-        dist.destroy_process_group()
+    ranks.close()
 
 
 if __name__ == "__main__":

@@ -66,6 +66,8 @@ SYMBOLS = {
     "chrom_cuda_table_stages": (C.c_uint32, [C.c_int32]),
     "chrom_cuda_tabulate_injection": (C.c_int32, [C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32,
                                                   C.c_double, C.c_uint64, _dp]),
+    "chrom_cuda_shard_range": (None, [C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64),
+                                      C.POINTER(C.c_uint64)]),
     "chrom_cuda_status_message": (C.c_size_t, [C.c_int64, C.c_char_p, C.c_size_t]),
     "chrom_cuda_solve_single_batch": (C.c_int32, [_vp, C.POINTER(RunCfg), C.POINTER(SingleCol), C.c_uint64, _dp,
                                                   C.c_uint32, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int64)]),

@@ -4,6 +4,7 @@
 //
 // Sharding: columns are independent, so a batch is cut into contiguous column
 // ranges, one per device of the context; each device has its own stream; there is no collective.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -294,15 +295,15 @@ int32_t make_plan(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, bool multi, con
   plan->series = n;
 
   const uint64_t G = ctx->devs.size();
-  const uint64_t per = (n_cols + G - 1) / G;
   const double t0 = now_ms();
   for (uint64_t gidx = 0; gidx < G; ++gidx) {
-    const uint64_t c0 = gidx * per;
-    if (c0 >= n_cols) break;
+    uint64_t c0 = 0, cnt = 0;
+    chrom_cuda_shard_range(n_cols, (uint32_t)G, (uint32_t)gidx, &c0, &cnt);
+    if (cnt == 0) break;
     std::unique_ptr<Shard> sh(new Shard);
     sh->dev = (int)gidx;
     sh->col0 = c0;
-    sh->n_cols = std::min(per, n_cols - c0);
+    sh->n_cols = cnt;
     if (int32_t rc = build_shard(plan.get(), *sh, scols, mcols, species, inj_tables, n_tables, y0)) return rc;
     plan->shards.push_back(std::move(sh));
   }
@@ -439,6 +440,15 @@ void chrom_cuda_time_points(double total_time, uint64_t time_steps, double* out)
   const double dt = total_time / (double)time_steps;
   out[0] = 0.0;                                                                   // rk4.rs:254
   for (uint64_t s = 0; s < time_steps; ++s) out[s + 1] = ((double)s + 1.0) * dt;  // rk4.rs:327
+}
+
+void chrom_cuda_shard_range(uint64_t n_cols, uint32_t n_devices, uint32_t device_index, uint64_t* col0,
+                            uint64_t* count) {
+  const uint64_t G = n_devices ? n_devices : 1;
+  const uint64_t per = (n_cols + G - 1) / G;
+  const uint64_t c0 = std::min<uint64_t>((uint64_t)device_index * per, n_cols);
+  if (col0) *col0 = c0;
+  if (count) *count = std::min<uint64_t>(per, n_cols - c0);
 }
 
 uint32_t chrom_cuda_table_stages(int32_t method) { return method == CHROM_RK4 ? 3u : 1u; }

@@ -123,6 +123,10 @@ uint32_t chrom_cuda_table_stages(int32_t method);
 /* Fills out[time_steps][stages] with TemporalInjection::evaluate at the solver's stage times. */
 int32_t chrom_cuda_tabulate_injection(int32_t kind, double p0, double p1, double p2, int32_t method,
                                       double total_time, uint64_t time_steps, double* out);
+/* The contiguous column range device `device_index` of `n_devices` owns in a batch of n_cols
+ * (ceil(n_cols / n_devices) columns per device, trailing devices may get fewer or none). */
+void chrom_cuda_shard_range(uint64_t n_cols, uint32_t n_devices, uint32_t device_index, uint64_t* col0,
+                            uint64_t* count);
 /* The reference's validate_state error string for a nonzero status (0 bytes written when status == 0).
  * Returns the length the full message needs. */
 size_t chrom_cuda_status_message(int64_t status, char* buf, size_t buf_len);
