@@ -9,6 +9,10 @@
 
 namespace chrom {
 
+// Kernel-internal arithmetic selector carried in BatchDev::arith: the two public modes plus the
+// polynomial FAST variant the host may substitute for CHROM_ARITH_FAST on single-species batches.
+#define CHROM_KARITH_POLY 2
+
 // Everything one device shard of a batch needs; all pointers are device pointers.
 struct BatchDev {
   // inputs
@@ -48,6 +52,7 @@ struct LaunchGeom {
   dim3 grid, block;
   size_t smem = 0;
   uint64_t launches_per_execute = 1;
+  uint32_t cols_per_wave = 0;  // columns one full wave of CTAs covers (0: the path is not chunkable)
   std::string name;
 };
 

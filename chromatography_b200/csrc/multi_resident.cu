@@ -522,7 +522,6 @@ size_t multi_smem_bytes(int n, uint32_t nz) {
 }  // namespace
 
 bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why) {
-  (void)sm_count;
   const int n = (int)b.n_species;
   if (n < 1 || n > 8) {
     if (why) *why = "n_species outside 1..8 (per-thread register LU); the warp-per-cell path is not built yet";
@@ -546,6 +545,11 @@ bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::
   g->block = dim3(T);
   g->grid = dim3(b.n_cols);
   g->smem = smem;
+  {
+    const int by_smem = (int)((227u * 1024u) / (smem + 1024));
+    const int by_regs = 65536 / (T * (n >= 8 ? 232 : (n >= 5 ? 200 : 128)));
+    g->cols_per_wave = (uint32_t)(sm_count * std::max(1, std::min(by_smem, by_regs)));
+  }
   char buf[200];
   snprintf(buf, sizeof buf, "multi_resident<n=%d,%s,%s> threads/col=%d cells/thread=%d smem=%zuB grid=%u", n,
            b.method == CHROM_RK4 ? "RK4" : "Euler", b.arith == CHROM_ARITH_EXACT ? "exact" : "fast", T, cpt, smem,
@@ -559,7 +563,7 @@ cudaError_t multi_resident_launch(const BatchDev& b, const LaunchGeom& g, cudaSt
   if (!k) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return e;
-  k<<<g.grid, g.block, g.smem, s>>>(b);
+  k<<<dim3(b.n_cols), g.block, g.smem, s>>>(b);
   return cudaGetLastError();
 }
 

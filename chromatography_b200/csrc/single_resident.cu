@@ -28,17 +28,19 @@
 namespace chrom {
 namespace {
 
+const char* arith_name(int a) { return a == CHROM_ARITH_EXACT ? "exact" : (a == CHROM_KARITH_POLY ? "fast-poly" : "fast"); }
+
 constexpr int kBlockThreads = 64;  // single-warp-per-column variant: 2 independent warps per CTA
 
 constexpr int min_blocks_for(int M) { return M >= 17 ? 4 : (M >= 11 ? 6 : 8); }
 // multi-warp variant: threads per CTA the register file allows for M cells per lane
 constexpr int mw_max_threads(int M) { return M <= 8 ? 512 : 256; }
 
-template <int M, int METHOD, bool EXACT, bool MW>
+template <int M, int METHOD, int ARITH, bool MW>
 __global__ void __launch_bounds__(MW ? mw_max_threads(M) : kBlockThreads, MW ? 1 : min_blocks_for(M))
     k_single_resident(const BatchDev b, const int L, const int cpw) {
   constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
-  using Q = Coef<EXACT>;
+  using Q = Coef<ARITH>;
   __shared__ double halo[2][32];
 
   const int lane = threadIdx.x & 31;
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(MW ? mw_max_threads(M) : kBlockThreads, MW ? 1
       }
     }
 
+    unsigned mx = 0u;  // max |high word| of the new state: the non-finite test, on the integer pipe
     if (METHOD == CHROM_RK4) {
       // stage 1: k1 = f(y, t)            acc = k1            u = y + k1*(dt/2)
       double up = exchange(y[M - 1], cin0, 0);
@@ -171,6 +174,7 @@ __global__ void __launch_bounds__(MW ? mw_max_threads(M) : kBlockThreads, MW ? 1
       for (int j = M - 1; j >= 0; --j) {
         const double k = q.rhs(u[j], j > 0 ? u[j - 1] : up);
         y[j] = Q::axpy(y[j], Q::add(acc[j], k), h6);
+        mx = max(mx, abs_hi(y[j]));
       }
     } else {
       // forward Euler: y = y + f(y, t)*dt
@@ -179,6 +183,7 @@ __global__ void __launch_bounds__(MW ? mw_max_threads(M) : kBlockThreads, MW ? 1
       for (int j = M - 1; j >= 0; --j) {
         const double k = q.rhs(y[j], j > 0 ? y[j - 1] : up);
         y[j] = Q::axpy(y[j], k, dt);
+        mx = max(mx, abs_hi(y[j]));
       }
     }
 
@@ -209,29 +214,37 @@ __global__ void __launch_bounds__(MW ? mw_max_threads(M) : kBlockThreads, MW ? 1
       ++snap_slot;
     }
 
-    // ---- validate_state (solver/mod.rs:514-553) on the integer pipe -------------------------
-    unsigned mx = 0u;
-#pragma unroll
-    for (int j = 0; j < M; ++j) mx = max(mx, j < nv ? abs_hi(y[j]) : 0u);
-    const bool bad = active && hi_nonfinite(mx);
+    // ---- validate_state (solver/mod.rs:514-553) ---------------------------------------------------
+    // Fast test over every cell of the lane, padding included (mx, accumulated inside the last stage);
+    // only when it fires is the state re-examined cell by cell, real cells only, NaN before Inf.
+    const bool maybe = hi_nonfinite(mx);
     if (MW) {
-      if (__syncthreads_or(bad) && !done) {
-        bool has_nan = false;
+      if (__syncthreads_or(maybe)) {
+        bool bad = false, has_nan = false;
 #pragma unroll
-        for (int j = 0; j < M; ++j) has_nan |= (j < nv) && (y[j] != y[j]);
+        for (int j = 0; j < M; ++j) {
+          bad |= (j < nv) && hi_nonfinite(abs_hi(y[j]));
+          has_nan |= (j < nv) && (y[j] != y[j]);
+        }
+        const int any_bad = __syncthreads_or(bad);
         const int any_nan = __syncthreads_or(has_nan);
-        if (threadIdx.x == 0 && b.status)
-          b.status[col] = any_nan ? (long long)(step + 1) : -(long long)(step + 1);
-        done = true;
+        if (any_bad && !done) {
+          if (threadIdx.x == 0 && b.status)
+            b.status[col] = any_nan ? (long long)(step + 1) : -(long long)(step + 1);
+          done = true;
+        }
       }
     } else {
-      const unsigned ballot = __ballot_sync(0xffffffffu, bad);
-      if (ballot != 0u) {
-        bool has_nan = false;
+      if (__ballot_sync(0xffffffffu, maybe) != 0u) {
+        bool bad = false, has_nan = false;
 #pragma unroll
-        for (int j = 0; j < M; ++j) has_nan |= (j < nv) && (y[j] != y[j]);
+        for (int j = 0; j < M; ++j) {
+          bad |= (j < nv) && hi_nonfinite(abs_hi(y[j]));
+          has_nan |= (j < nv) && (y[j] != y[j]);
+        }
+        const unsigned bad_ballot = __ballot_sync(0xffffffffu, bad && active);
         const unsigned nan_ballot = __ballot_sync(0xffffffffu, has_nan && active);
-        if ((ballot & gmask) != 0u && !done) {
+        if ((bad_ballot & gmask) != 0u && !done) {
           if (p == 0 && active && b.status)
             b.status[col] = (nan_ballot & gmask) ? (long long)(step + 1) : -(long long)(step + 1);
           done = true;
@@ -255,14 +268,15 @@ typedef void (*kern_t)(const BatchDev, const int, const int);
 
 template <int M, bool MW>
 kern_t pick(int method, int arith) {
-  if (method == CHROM_RK4)
-    return arith == CHROM_ARITH_EXACT ? k_single_resident<M, CHROM_RK4, true, MW>
-                                      : k_single_resident<M, CHROM_RK4, false, MW>;
-  return arith == CHROM_ARITH_EXACT ? k_single_resident<M, CHROM_EULER, true, MW>
-                                    : k_single_resident<M, CHROM_EULER, false, MW>;
+  if (method == CHROM_RK4) {
+    if (arith == CHROM_ARITH_EXACT) return k_single_resident<M, CHROM_RK4, 1, MW>;
+    return arith == CHROM_KARITH_POLY ? k_single_resident<M, CHROM_RK4, 2, MW> : k_single_resident<M, CHROM_RK4, 0, MW>;
+  }
+  if (arith == CHROM_ARITH_EXACT) return k_single_resident<M, CHROM_EULER, 1, MW>;
+  return arith == CHROM_KARITH_POLY ? k_single_resident<M, CHROM_EULER, 2, MW> : k_single_resident<M, CHROM_EULER, 0, MW>;
 }
 
-const int kM[] = {2, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 25, 28, 32};
+const int kM[] = {2, 4, 5, 6, 7, 8, 10, 12, 13, 14, 16, 17, 20, 25, 28, 32};
 const int kMmw[] = {8, 16, 32};
 
 kern_t lookup(int M, bool mw, int method, int arith) {
@@ -283,8 +297,10 @@ kern_t lookup(int M, bool mw, int method, int arith) {
     case 8: return pick<8, false>(method, arith);
     case 10: return pick<10, false>(method, arith);
     case 12: return pick<12, false>(method, arith);
+    case 13: return pick<13, false>(method, arith);
     case 14: return pick<14, false>(method, arith);
     case 16: return pick<16, false>(method, arith);
+    case 17: return pick<17, false>(method, arith);
     case 20: return pick<20, false>(method, arith);
     case 25: return pick<25, false>(method, arith);
     case 28: return pick<28, false>(method, arith);
@@ -339,8 +355,9 @@ bool single_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std:
     g->block = dim3(kBlockThreads);
     g->grid = dim3((unsigned)((warps + (kBlockThreads / 32) - 1) / (kBlockThreads / 32)));
     g->smem = 0;
+    g->cols_per_wave = (uint32_t)(sm_count * min_blocks_for(bestM) * (kBlockThreads / 32) * bestCpw);
     snprintf(buf, sizeof buf, "single_resident<M=%d,%s,%s> lanes/col=%d cols/warp=%d grid=%u block=%d",
-             bestM, b.method == CHROM_RK4 ? "RK4" : "Euler", b.arith == CHROM_ARITH_EXACT ? "exact" : "fast",
+             bestM, b.method == CHROM_RK4 ? "RK4" : "Euler", arith_name(b.arith),
              bestL, bestCpw, g->grid.x, kBlockThreads);
     g->name = buf;
     return true;
@@ -367,8 +384,9 @@ bool single_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std:
   g->block = dim3(bestW * 32);
   g->grid = dim3(b.n_cols);
   g->smem = 0;
+  g->cols_per_wave = (uint32_t)(sm_count * std::max(1, 512 / (bestW * 32)));
   snprintf(buf, sizeof buf, "single_resident_mw<M=%d,%s,%s> warps/col=%d grid=%u block=%d", bestM,
-           b.method == CHROM_RK4 ? "RK4" : "Euler", b.arith == CHROM_ARITH_EXACT ? "exact" : "fast", bestW,
+           b.method == CHROM_RK4 ? "RK4" : "Euler", arith_name(b.arith), bestW,
            g->grid.x, bestW * 32);
   g->name = buf;
   return true;
@@ -377,7 +395,15 @@ bool single_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std:
 cudaError_t single_resident_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s) {
   kern_t k = lookup(g.M, g.kind == 2, b.method, b.arith);
   if (!k) return cudaErrorInvalidValue;
-  k<<<g.grid, g.block, g.smem, s>>>(b, g.L, g.cpw);
+  // grid from b.n_cols (a chunk of the planned batch may be launched on its own)
+  dim3 grid = g.grid;
+  if (g.kind == 1) {
+    const uint64_t warps = ((uint64_t)b.n_cols + g.cpw - 1) / g.cpw;
+    grid = dim3((unsigned)((warps + (kBlockThreads / 32) - 1) / (kBlockThreads / 32)));
+  } else {
+    grid = dim3(b.n_cols);
+  }
+  k<<<grid, g.block, g.smem, s>>>(b, g.L, g.cpw);
   return cudaGetLastError();
 }
 

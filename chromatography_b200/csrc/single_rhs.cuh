@@ -6,12 +6,14 @@
 
 namespace chrom {
 
-template <bool EXACT>
+// ARITH: 0 = FAST (no cancellation anywhere), 1 = EXACT (reference order), 2 = FAST_POLY (one instruction
+// fewer; chosen by the host when the isotherm is not extremely steep, see CHROM_KARITH_POLY in kernels.h)
+template <int ARITH>
 struct Coef;
 
 // EXACT: langmuir_single.rs:391-396, 409-412, 503-510, one IEEE op per reference op.
 template <>
-struct Coef<true> {
+struct Coef<1> {
   double K, nK, lambda, fe, ue, dz;
   __device__ __forceinline__ void init(const chrom_single_col& c) {
     // n_bar = fe / (1.0 + fe) * port_number is loop-invariant: hoisting it gives the same bits.
@@ -37,7 +39,7 @@ struct Coef<true> {
 // FAST: sigma*(-ue/dz)*(c-up) = (c-up)*d2 / (A'*d2 + B'),  d = 1+K*c, d2 = d*d,
 //       A' = (1+fe*lambda)/Cg, B' = fe*n_bar*K/Cg, Cg = -ue/dz.   9 DFMA-pipe ops + 1 MUFU.
 template <>
-struct Coef<false> {
+struct Coef<0> {
   double K, Ap, Bp;
   __device__ __forceinline__ void init(const chrom_single_col& c) {
     const double n_bar = c.fe / (1.0 + c.fe) * c.port_number;
@@ -55,6 +57,44 @@ struct Coef<false> {
     const double r = fast_rcp(den);
     const double g = c - up;
     return (g * d2) * r;
+  }
+  static __device__ __forceinline__ double axpy(double y, double k, double h) { return fma(k, h, y); }
+  static __device__ __forceinline__ double add(double a, double b) { return a + b; }
+};
+
+// FAST_POLY: the same function with the denominator as a Horner polynomial in c and the quotient
+// split off its constant part:
+//   sigma' = d2/(A'd2 + B') = c1 - 1/P(c),  c1 = 1/A',  P(c) = (A'd2 + B')/c2,  c2 = B'/A',
+//   P(c) = p0 + c*(p1 + p2*c),  p0 = (A'+B')/c2, p1 = 2A'K/c2, p2 = A'K^2/c2.
+// 8 FP64-pipe ops + 1 MUFU per cell-stage (2 FMA for P, 3 for the reciprocal, c1 - x, c - up, product).
+// c1 - x cancels by a factor 1 + B/(A d2) <= 1 + B/A, so the host selects this form only when
+// B/A = fe*n_bar*K/(1+fe*lambda) <= 1e3 (relative error <= ~1e-13, far inside 1e-9).
+template <>
+struct Coef<2> {
+  double p0, p1, p2, c1;
+  __device__ __forceinline__ void init(const chrom_single_col& c) {
+    const double n_bar = c.fe / (1.0 + c.fe) * c.port_number;
+    const double A = 1.0 + c.fe * c.lambda;
+    const double B = c.fe * (n_bar * c.langmuir_k);
+    const double Cg = -c.ue / c.dz;
+    const double Ap = A / Cg, Bp = B / Cg, K = c.langmuir_k;
+    c1 = 1.0 / Ap;
+    if (B != 0.0) {
+      const double c2 = Bp / Ap;
+      p0 = (Ap + Bp) / c2;
+      p1 = 2.0 * Ap * K / c2;
+      p2 = Ap * K * K / c2;
+    } else {  // linear isotherm: sigma' = c1 exactly; 1/P underflows to nothing
+      p0 = -1e300;
+      p1 = 0.0;
+      p2 = 0.0;
+    }
+  }
+  __device__ __forceinline__ double rhs(double c, double up) const {
+    const double P = fma(c, fma(p2, c, p1), p0);
+    const double x = fast_rcp(P);
+    const double g = c - up;
+    return g * (c1 - x);
   }
   static __device__ __forceinline__ double axpy(double y, double k, double h) { return fma(k, h, y); }
   static __device__ __forceinline__ double add(double a, double b) { return a + b; }

@@ -27,14 +27,14 @@ constexpr int kWarps = 4;       // warps per CTA
 
 // status word while streaming: 0 = clean, else (step << 1) | has_nan; atomicMax keeps NaN over Inf
 // within a step, later steps never overwrite (solver/mod.rs:519-548: NaN wins, first step wins).
-template <int METHOD, bool EXACT>
+template <int METHOD, int ARITH>
 __global__ void __launch_bounds__(kWarps * 32)
     k_single_stream_step(const BatchDev b, const double* __restrict__ src, double* __restrict__ dst, uint32_t step,
                          unsigned long long* __restrict__ code, int out_slot, int tiles_per_col) {
   constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
   constexpr int H = (METHOD == CHROM_RK4) ? 4 : 0;  // RK4 stage values reach 4 cells upstream
   constexpr int V = kTile - H;  // cells a non-first tile contributes
-  using Q = Coef<EXACT>;
+  using Q = Coef<ARITH>;
   const int lane = threadIdx.x & 31;
   const int tile = (int)(blockIdx.x * kWarps + (threadIdx.x >> 5));
   const uint32_t col = blockIdx.y;
@@ -198,10 +198,12 @@ __global__ void k_stream_init(const BatchDev b, double* __restrict__ ping, unsig
 typedef void (*skern_t)(const BatchDev, const double*, double*, uint32_t, unsigned long long*, int, int);
 
 skern_t pick_stream(int method, int arith) {
-  if (method == CHROM_RK4)
-    return arith == CHROM_ARITH_EXACT ? k_single_stream_step<CHROM_RK4, true> : k_single_stream_step<CHROM_RK4, false>;
-  return arith == CHROM_ARITH_EXACT ? k_single_stream_step<CHROM_EULER, true>
-                                    : k_single_stream_step<CHROM_EULER, false>;
+  if (method == CHROM_RK4) {
+    if (arith == CHROM_ARITH_EXACT) return k_single_stream_step<CHROM_RK4, 1>;
+    return arith == CHROM_KARITH_POLY ? k_single_stream_step<CHROM_RK4, 2> : k_single_stream_step<CHROM_RK4, 0>;
+  }
+  if (arith == CHROM_ARITH_EXACT) return k_single_stream_step<CHROM_EULER, 1>;
+  return arith == CHROM_KARITH_POLY ? k_single_stream_step<CHROM_EULER, 2> : k_single_stream_step<CHROM_EULER, 0>;
 }
 
 }  // namespace
@@ -224,7 +226,7 @@ bool single_stream_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::s
   g->launches_per_execute = (uint64_t)b.steps + 2;
   char buf[200];
   snprintf(buf, sizeof buf, "single_stream<M=%d,%s,%s> tiles/col=%d halo=%d grid=(%u,%u) block=%d, 1 launch per step", kM,
-           b.method == CHROM_RK4 ? "RK4" : "Euler", b.arith == CHROM_ARITH_EXACT ? "exact" : "fast", tiles, H, g->grid.x,
+           b.method == CHROM_RK4 ? "RK4" : "Euler", (b.arith == CHROM_ARITH_EXACT ? "exact" : (b.arith == CHROM_KARITH_POLY ? "fast-poly" : "fast")), tiles, H, g->grid.x,
            g->grid.y, kWarps * 32);
   g->name = buf;
   return true;

@@ -225,3 +225,34 @@ def test_plan_reexecution_is_deterministic(ctx):
     assert t1["kernel_ms"] > 0 and t1["kernel_launches"] == 1
     assert_bit_equal(a.final_state, b.final_state, "re-execution")
     plan.close()
+
+
+def test_pipelined_one_shot_equals_plan_and_oracle(ctx):
+    """A batch large enough for the chunked compute / copy-back pipeline of the one-shot solve
+    (>= 2 waves of columns, >= 64 MB of outputs) must give the same bits as the plan path (one launch)
+    and match the oracle on a sample of columns."""
+    n_cols, T, steps = 20_000, 30.0, 500
+    a = W.tfa_sweep_arrays(n_cols, seed=7)
+    from chromatography_b200 import _ffi
+    cols = (_ffi.SingleCol * n_cols)()
+    arr = np.frombuffer(cols, dtype=np.float64).reshape(n_cols, 7)
+    for j, k in enumerate(["lambda_", "langmuir_k", "port_number", "fe", "ue", "dz"]):
+        arr[:, j] = a[k]
+    arr[:, 6] = 0.0
+    tables = cb.tabulate_injection(cb.TemporalInjection.gaussian(10.0, 3.0, 0.1), cb.RK4, T, steps)[None]
+    cfg = cb.make_cfg(cb.RK4, T, steps, 100, arith=cb.ARITH_EXACT)
+    one = cb.solve_single_batch(ctx, cfg, cols, tables, want_summary=True)
+    assert one.timing["kernel_launches"] > 1, "expected the chunked pipeline"
+    plan = cb.Plan(ctx, cfg, cols, tables, want=cb.WANT_OUTLET | cb.WANT_FINAL | cb.WANT_STATUS | cb.WANT_SUMMARY)
+    plan.execute()
+    ref = plan.download()
+    plan.close()
+    assert_bit_equal(one.outlet, ref.outlet, "outlet")
+    assert_bit_equal(one.final_state, ref.final_state, "final")
+    assert_bit_equal(one.summary, ref.summary, "summary")
+    assert not one.status.any()
+    pick = [0, 1, 9471, 9472, 9473, 18943, 18944, 19_999]
+    models = W.tfa_sweep_models(n_cols, seed=7)
+    oo, of, _ = O.solve_single_batch([to_oracle(models[i]) for i in pick], O.RK4, T, steps)
+    assert_bit_equal(one.outlet[pick], oo, "outlet vs oracle")
+    assert_bit_equal(one.final_state[pick], of, "final vs oracle")
