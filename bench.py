@@ -290,6 +290,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--cols", type=int, default=0, help="override columns per GPU (debug only; invalidates the metric)")
+    ap.add_argument("--arith", default="fast", choices=["fast", "structured"],
+                    help="multi-species workloads: dense register LU (fast) or structured LU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -320,7 +322,12 @@ def main():
     inp = build_inputs(spec, n_cols, rank)
     n_cols = len(inp["cols"])
     units_rank = units_of(spec, n_cols)
-    cfg = cb.make_cfg(cb.RK4, inp["total_time"], spec["steps"], spec["nz"], spec["n_species"], 1, 0, cb.ARITH_FAST)
+    arith = cb.ARITH_FAST_STRUCTURED if (args.arith == "structured" and spec["kind"] == "multi") else cb.ARITH_FAST
+    if arith == cb.ARITH_FAST_STRUCTURED:
+        # structured LU: ~28 flops per species per cell-stage (4 setup, 2 pivot bound, 15 forward incl. one
+        # reciprocal, 3 back substitution, 3.25 stage algebra) + 8 per cell; the 776 of SURVEY §8d is dense LU
+        spec = dict(spec, flops=28.0 * spec["n_species"] + 8.0)
+    cfg = cb.make_cfg(cb.RK4, inp["total_time"], spec["steps"], spec["nz"], spec["n_species"], 1, 0, arith)
     want = cb.WANT_OUTLET | cb.WANT_FINAL | cb.WANT_STATUS
 
     # ---- value: inputs resident in HBM --------------------------------------------------------------

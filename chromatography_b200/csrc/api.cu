@@ -93,7 +93,7 @@ struct Shard {
   DevBuf<chrom_single_col> scols;
   DevBuf<chrom_multi_col> mcols;
   DevBuf<chrom_species> species;
-  DevBuf<double> tables, y0, outlet, snapshots, final_state, summary, ping, pong;
+  DevBuf<double> tables, y0, outlet, snapshots, final_state, summary, ping, pong, scratch;
   DevBuf<long long> status;
   BatchDev b{};
   LaunchGeom g;
@@ -148,7 +148,8 @@ int32_t check_cfg(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, bool multi) {
   if (const char* m = chrom_cuda_validate_cfg(cfg)) return fail(ctx, CHROM_ERR_INVALID, m);
   if (cfg->method != CHROM_EULER && cfg->method != CHROM_RK4)
     return fail(ctx, CHROM_ERR_INVALID, format("unknown method %d (0 = Euler, 1 = RK4)", cfg->method));
-  if (cfg->arith != CHROM_ARITH_FAST && cfg->arith != CHROM_ARITH_EXACT)
+  if (cfg->arith != CHROM_ARITH_FAST && cfg->arith != CHROM_ARITH_EXACT &&
+      !(multi && cfg->arith == CHROM_ARITH_FAST_STRUCTURED))
     return fail(ctx, CHROM_ERR_INVALID, format("unknown arith mode %d", cfg->arith));
   if (cfg->n_points < 2)
     return fail(ctx, CHROM_ERR_INVALID, format("Need at least 2 spatial points, got %u", cfg->n_points));
@@ -230,6 +231,7 @@ int32_t build_shard(chrom_cuda_plan* plan, Shard& sh, const chrom_single_col* sc
   b.summary = sh.summary.p;
   b.status = sh.status.p;
   b.ping = b.pong = nullptr;
+  b.scratch = nullptr;
   b.n_cols = (uint32_t)sh.n_cols;
   b.nz = cfg.n_points;
   b.n_species = cfg.n_species;
@@ -273,7 +275,15 @@ int32_t build_shard(chrom_cuda_plan* plan, Shard& sh, const chrom_single_col* sc
       b.pong = sh.pong.p;
     }
   } else {
+    b.arith = multi_kernel_arith((int)cfg.n_species, cfg.arith);
     ok = multi_resident_choose(b, d.sm_count, &sh.g, &why);
+    if (ok) {
+      const size_t per_thread = multi_scratch_per_thread((int)cfg.n_species, b.arith);
+      if (per_thread) {
+        CUDA_TRY(ctx, sh.scratch.alloc(per_thread * sh.g.grid.x * sh.g.block.x, d.stream));
+        b.scratch = sh.scratch.p;
+      }
+    }
   }
   if (!ok) return fail(ctx, CHROM_ERR_UNSUPPORTED, "no kernel covers this shape: " + why);
   return CHROM_OK;

@@ -12,6 +12,7 @@ namespace chrom {
 // Kernel-internal arithmetic selector carried in BatchDev::arith: the two public modes plus the
 // polynomial FAST variant the host may substitute for CHROM_ARITH_FAST on single-species batches.
 #define CHROM_KARITH_POLY 2
+#define CHROM_KARITH_STRUCT 3  /* multi-species: structured (diag + rank-1) LU, see multi_resident.cu */
 
 // Everything one device shard of a batch needs; all pointers are device pointers.
 struct BatchDev {
@@ -30,6 +31,7 @@ struct BatchDev {
   // streaming path scratch: two state buffers [n_cols][nz]
   double* ping;
   double* pong;
+  double* scratch;  // multi-species n > 8: per-thread dense-matrix scratch (see multi_scratch_per_thread)
   // shape
   uint32_t n_cols;
   uint32_t nz;
@@ -67,6 +69,8 @@ cudaError_t single_stream_launch(const BatchDev& b, const LaunchGeom& g, cudaStr
 // multi_resident.cu — LangmuirMulti, per-cell n x n solve
 bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why);
 cudaError_t multi_resident_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s);
+int multi_kernel_arith(int n_species, int arith);
+size_t multi_scratch_per_thread(int n_species, int kernel_arith);
 
 // probe.cu
 cudaError_t measure_fp64_peak(int sm_count, cudaStream_t s, double* tflops, double* ms);

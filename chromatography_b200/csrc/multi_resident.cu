@@ -20,6 +20,7 @@
 // One __syncthreads per stage; the last one of a step carries the non-finite flag.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "arith.cuh"
 #include "kernels.h"
@@ -27,10 +28,16 @@
 namespace chrom {
 namespace {
 
-struct SpeciesConst {  // per species, shared memory
-  double lambda, K, nbar;  // nbar = stationary_fraction * (double)port_number
-  double a0;               // FAST: 1 + fe*lambda
-  double feNK;             // FAST: fe * nbar * K
+constexpr int kNMax = 64;      // largest runtime n
+constexpr int kNMaxDecl = kNMax;
+
+struct alignas(16) SpeciesConst {  // per species, shared memory; {K, feNK} and {a0, feNK2} load as 128-bit pairs
+  double K;      // langmuir_k
+  double feNK;   // FAST: fe * nbar * K
+  double a0;     // FAST: 1 + fe*lambda
+  double feNK2;  // = feNK (second copy so that the forward sweep needs one 128-bit load)
+  double lambda;
+  double nbar;   // stationary_fraction * (double)port_number
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -311,194 +318,547 @@ __device__ __forceinline__ void fast_row(const SpeciesConst* sc, double fe, doub
   }
 }
 
-constexpr int multi_max_threads(int N) { return N <= 2 ? 512 : 256; }
+// ------------------------------------------------------------------------------------------------
+// STRUCTURED: Gaussian elimination with partial pivoting on A = diag(alpha) - p q^T WITHOUT forming
+// the matrix.  Eliminating column i of diag(alpha) - g p q^T leaves diag(alpha') - g' p' q'^T on the
+// trailing block with g' = g * alpha_i / d_i, d_i = alpha_i - g p_i q_i (the pivot), so L, U and the
+// solve need O(n) scalars:  U[i][c] = -g_i p_i q_c,  L[r][i] = -g_i p_r q_i / d_i.
+// The pivot test of partial pivoting, |L[r][i] d_i| > |d_i| for some r > i, becomes
+// g_i q_i max_{r>i} |p_r| > |d_i|; when it fires the caller redoes the cell with the dense
+// row-exchanging LU (register LU for n <= 8, scratch-memory LU beyond).  Same pivots, same factors,
+// O(n) registers: this is what makes n > 8 fit a thread and lets two warps more per SM fly.
+// N > 0: compile-time n (registers); N == 0: runtime n (local arrays of kNMax).
+// ------------------------------------------------------------------------------------------------
 
-template <int N, int METHOD, bool EXACT>
-__global__ void __launch_bounds__(multi_max_threads(N), 1) k_multi_resident(const BatchDev b) {
+// Compile-time n: everything in registers, 4n doubles of state (K, p -> g*p, rhs -> x, suffix max ->
+// reciprocal pivot), two 128-bit shared loads of constants per species.  Reads the cell from shared
+// memory itself; the solution is left in x[].
+template <int N>
+__device__ __forceinline__ bool structured_cell(const SpeciesConst* sc, double cg, const double* SRC,
+                                                const double* inlet_row, uint32_t nz, uint32_t cc, double (&x)[N]) {
+  double K[N], pw[N], d[N];
+  double S = 0.0;
+#pragma unroll
+  for (int s = 0; s < N; ++s) {
+    const double c = SRC[(size_t)s * nz + cc];
+    const double up = (cc > 0) ? SRC[(size_t)s * nz + cc - 1] : inlet_row[s];
+    const double2 kf = *reinterpret_cast<const double2*>(&sc[s].K);  // {K, feNK}
+    K[s] = kf.x;
+    x[s] = (c - up) * cg;
+    S = fma(kf.x, c, S);
+    pw[s] = kf.y * c;  // feNK_s * c_s; p_s = pw_s / D^2
+  }
+  const double rD = fast_rcp(1.0 + S);
+  const double rD2 = rD * rD;
+  double sfx = 0.0;
+#pragma unroll
+  for (int s = N - 1; s >= 0; --s) {
+    d[s] = sfx * rD2;  // max_{r>s} |p_r|, parked until the forward sweep reaches s
+    sfx = fmax(sfx, fabs(pw[s]));
+  }
+  double g = 1.0, carry = 0.0;
+  bool redo = false;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double2 af = *reinterpret_cast<const double2*>(&sc[i].a0);  // {a0, feNK}
+    const double alpha = fma(af.y, rD, af.x);                        // 1 + fe*(lambda_i + nbar_i K_i / D)
+    const double p = pw[i] * rD2;
+    const double b_i = fma(p, carry, x[i]);
+    const double t = g * p;
+    const double piv = fma(-t, K[i], alpha);
+    const double gq = g * K[i];
+    redo |= (gq * d[i] > fabs(piv)) || (piv == 0.0);
+    const double rp = fast_rcp(piv);
+    pw[i] = t;
+    x[i] = b_i;
+    d[i] = rp;
+    carry = fma(gq * rp, b_i, carry);
+    g = g * (alpha * rp);
+  }
+  double Sx = 0.0;
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    const double xi = fma(pw[i], Sx, x[i]) * d[i];
+    x[i] = xi;
+    Sx = fma(K[i], xi, Sx);
+  }
+  return redo;
+}
+
+// Runtime n (9 .. kNMax): the same sweep over local arrays.
+template <int N>
+__device__ __forceinline__ bool structured_row(int n_rt, const SpeciesConst* sc, double cg, const double* c,
+                                               const double* up, double* k) {
+  constexpr int CAP = N > 0 ? N : kNMax;
+  const int n = N > 0 ? N : n_rt;
+  double S = 0.0;
+#pragma unroll
+  for (int s = 0; s < CAP; ++s)
+    if (s < n) S = fma(sc[s].K, c[s], S);
+  const double rD = fast_rcp(1.0 + S);
+  const double rD2 = rD * rD;
+  double p[CAP], d[CAP], gp[CAP], bb[CAP];  // p_i, reciprocal pivots, g_i*p_i, eliminated rhs
+  double pmax_suffix = 0.0;
+#pragma unroll
+  for (int s = CAP - 1; s >= 0; --s)
+    if (s < n) {
+      p[s] = sc[s].feNK * c[s] * rD2;
+      d[s] = pmax_suffix;  // max_{r>s} |p_r| parked here until the forward sweep reaches s
+      pmax_suffix = fmax(pmax_suffix, fabs(p[s]));
+    }
+  double g = 1.0, carry = 0.0;
+  bool need_pivot = false, singular = false;
+#pragma unroll
+  for (int i = 0; i < CAP; ++i)
+    if (i < n) {
+      const double q = sc[i].K;
+      const double alpha = fma(sc[i].feNK, rD, sc[i].a0);  // 1 + fe*(lambda_i + nbar_i K_i / D)
+      const double b_i = fma(p[i], carry, (c[i] - up[i]) * cg);
+      const double t = g * p[i];
+      const double piv = fma(-t, q, alpha);
+      const double gq = g * q;
+      need_pivot |= (gq * d[i] > fabs(piv));
+      singular |= (piv == 0.0);
+      const double rp = fast_rcp(piv);
+      gp[i] = t;
+      bb[i] = b_i;
+      d[i] = rp;
+      const double w = gq * rp;
+      carry = fma(w, b_i, carry);
+      g = g * (alpha * rp);
+    }
+  double Sx = 0.0;
+#pragma unroll
+  for (int i = CAP - 1; i >= 0; --i)
+    if (i < n) {
+      const double x = fma(gp[i], Sx, bb[i]) * d[i];
+      k[i] = x;
+      Sx = fma(sc[i].K, x, Sx);
+    }
+  return need_pivot || singular;
+}
+
+// Dense LU with partial pivoting for runtime n, matrix in per-thread scratch memory
+// (element e of this thread at a[e * stride]).  FAST arithmetic; only reached when the structured
+// sweep reports that a row exchange is needed (or an exactly singular pivot: identity fallback).
+__device__ void dense_row_scratch(int n, const SpeciesConst* sc, double cg, const double* c, const double* up,
+                                  double* k, double* a, size_t stride) {
+  auto A = [&](int i, int j) -> double& { return a[((size_t)i * n + j) * stride]; };
+  double S = 0.0;
+  for (int s = 0; s < n; ++s) S = fma(sc[s].K, c[s], S);
+  const double D = 1.0 + S, rD2 = 1.0 / (D * D);
+  for (int i = 0; i < n; ++i) {
+    const double p = sc[i].feNK * c[i] * rD2;
+    for (int j = 0; j < n; ++j) A(i, j) = -p * sc[j].K;
+    A(i, i) = fma(sc[i].feNK, D * rD2, sc[i].a0) + A(i, i);
+    k[i] = (c[i] - up[i]) * cg;
+  }
+  bool singular = false;
+  for (int i = 0; i < n; ++i) {
+    int piv = i;
+    double best = fabs(A(i, i));
+    for (int r = i + 1; r < n; ++r)
+      if (fabs(A(r, i)) > best) {
+        best = fabs(A(r, i));
+        piv = r;
+      }
+    if (piv != i) {
+      for (int q = i; q < n; ++q) {
+        const double t = A(i, q);
+        A(i, q) = A(piv, q);
+        A(piv, q) = t;
+      }
+      const double t = k[i];
+      k[i] = k[piv];
+      k[piv] = t;
+    }
+    singular |= (A(i, i) == 0.0);
+    const double rp = 1.0 / A(i, i);
+    for (int r = i + 1; r < n; ++r) {
+      const double l = A(r, i) * rp;
+      for (int q = i + 1; q < n; ++q) A(r, q) = fma(-l, A(i, q), A(r, q));
+      k[r] = fma(-l, k[i], k[r]);
+    }
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = k[i];
+    for (int q = i + 1; q < n; ++q) s = fma(-A(i, q), k[q], s);
+    k[i] = s / A(i, i);
+  }
+  if (singular)
+    for (int s = 0; s < n; ++s) k[s] = (c[s] - up[s]) * cg;
+}
+
+// EXACT for runtime n >= 5: compute_row with nalgebra's lu::try_invert_to and gemv, matrices in
+// per-thread scratch (mat, inverse, LU copy: 3 n^2 doubles).  Same operation order as exact_row<N>.
+__device__ void exact_row_scratch(int n, const SpeciesConst* sc, double fe, double ue, double dz, const double* c,
+                                  const double* up, double* k, double* scratch, size_t stride) {
+  const size_t nn = (size_t)n * n;
+  auto M = [&](int i, int j) -> double& { return scratch[((size_t)i + (size_t)j * n) * stride]; };             // mat
+  auto O = [&](int i, int j) -> double& { return scratch[(nn + (size_t)i + (size_t)j * n) * stride]; };        // inverse
+  auto A = [&](int i, int j) -> double& { return scratch[(2 * nn + (size_t)i + (size_t)j * n) * stride]; };    // LU copy
+  double sum_kc = 0.0;
+  for (int s = 0; s < n; ++s) sum_kc = x_add(sum_kc, x_mul(sc[s].K, c[s]));
+  const double denom = x_add(1.0, sum_kc);
+  const double denom2 = x_mul(denom, denom);
+  for (int i = 0; i < n; ++i) {
+    const double nb = sc[i].nbar, Ki = sc[i].K;
+    for (int j = 0; j < n; ++j) {
+      double J;
+      if (i == j) {
+        const double num = x_mul(x_mul(nb, Ki), x_sub(denom, x_mul(Ki, c[i])));
+        J = x_add(sc[i].lambda, x_div(num, denom2));
+      } else {
+        const double num = x_mul(x_mul(x_mul(-nb, Ki), sc[j].K), c[i]);
+        J = x_div(num, denom2);
+      }
+      M(i, j) = x_add((i == j) ? 1.0 : 0.0, x_mul(fe, J));
+    }
+  }
+  // lu::try_invert_to
+  bool ok = true;
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i) {
+      A(i, j) = M(i, j);
+      O(i, j) = (i == j) ? 1.0 : 0.0;
+    }
+  for (int i = 0; i < n && ok; ++i) {
+    int piv = i;
+    double the_max = fabs(A(i, i));
+    for (int r = i + 1; r < n; ++r) {
+      const double v = fabs(A(r, i));
+      if (v > the_max) {
+        the_max = v;
+        piv = r;
+      }
+    }
+    const double diag = A(piv, i);
+    if (diag == 0.0) {
+      ok = false;
+      break;
+    }
+    if (piv != i) {
+      for (int j = 0; j < n; ++j) {
+        const double t = O(i, j);
+        O(i, j) = O(piv, j);
+        O(piv, j) = t;
+      }
+      for (int j = 0; j <= i; ++j) {
+        const double t = A(i, j);
+        A(i, j) = A(piv, j);
+        A(piv, j) = t;
+      }
+    }
+    const double inv_diag = x_div(1.0, diag);
+    for (int r = i + 1; r < n; ++r) A(r, i) = x_mul(A(r, i), inv_diag);
+    for (int q = i + 1; q < n; ++q) {
+      if (piv != i) {
+        const double t = A(i, q);
+        A(i, q) = A(piv, q);
+        A(piv, q) = t;
+      }
+      const double neg_pivot = -A(i, q);
+      for (int r = i + 1; r < n; ++r) A(r, q) = x_add(x_mul(neg_pivot, A(r, i)), A(r, q));
+    }
+  }
+  if (ok) {
+    for (int cc = 0; cc < n; ++cc)
+      for (int i = 0; i + 1 < n; ++i) {
+        const double coeff = O(i, cc);
+        for (int r = i + 1; r < n; ++r) O(r, cc) = x_add(x_mul(-coeff, A(r, i)), O(r, cc));
+      }
+    for (int cc = 0; cc < n && ok; ++cc)
+      for (int i = n - 1; i >= 0; --i) {
+        const double diag = A(i, i);
+        if (diag == 0.0) {
+          ok = false;
+          break;
+        }
+        const double coeff = x_div(O(i, cc), diag);
+        O(i, cc) = coeff;
+        for (int r = 0; r < i; ++r) O(r, cc) = x_add(x_mul(-coeff, A(r, i)), O(r, cc));
+      }
+  }
+  if (!ok)  // identity fallback, langmuir_multi.rs:790-796
+    for (int j = 0; j < n; ++j)
+      for (int i = 0; i < n; ++i) O(i, j) = (i == j) ? 1.0 : 0.0;
+  // grad, gemv (column by column, j ascending), scale
+  for (int i = 0; i < n; ++i) k[i] = x_mul(O(i, 0), x_div(x_sub(c[0], up[0]), dz));
+  for (int j = 1; j < n; ++j) {
+    const double gj = x_div(x_sub(c[j], up[j]), dz);
+    for (int i = 0; i < n; ++i) k[i] = x_add(x_mul(O(i, j), gj), k[i]);
+  }
+  for (int s = 0; s < n; ++s) k[s] = x_mul(-ue, k[s]);
+}
+
+// Stage algebra of one cell (all species) on the shared-memory state.  Returns the non-finite flag of
+// the new state where the stage produces one.
+struct StageCtx {
+  double* Y;
+  double* ACC;
+  double* DST;
+  uint32_t nz;
+  int stage;  // 0 Euler, 1..4 RK4
+  double dt, h2, h6;
+};
+
+template <int N, bool EXACT>
+__device__ __forceinline__ bool apply_stage(const StageCtx& st, uint32_t cc, const double* k, int n_rt) {
+  constexpr int CAP = N > 0 ? N : kNMaxDecl;
+  const int n = N > 0 ? N : n_rt;
+  auto axpy = [](double y, double kk, double h) { return EXACT ? x_add(y, x_mul(kk, h)) : fma(kk, h, y); };
+  bool bad = false;
+#pragma unroll
+  for (int s = 0; s < CAP; ++s)
+    if (s < n) {
+      const size_t idx = (size_t)s * st.nz + cc;
+      if (st.stage == 0) {
+        const double yn = axpy(st.Y[idx], k[s], st.dt);
+        st.Y[idx] = yn;  // Euler reads SRC = U0/U1 (a copy of Y), so Y can be overwritten
+        st.DST[idx] = yn;
+        bad |= hi_nonfinite(abs_hi(yn));
+      } else if (st.stage == 1) {
+        st.ACC[idx] = k[s];
+        st.DST[idx] = axpy(st.Y[idx], k[s], st.h2);
+      } else if (st.stage == 2) {
+        st.ACC[idx] = axpy(st.ACC[idx], k[s], 2.0);
+        st.DST[idx] = axpy(st.Y[idx], k[s], st.h2);
+      } else if (st.stage == 3) {
+        st.ACC[idx] = axpy(st.ACC[idx], k[s], 2.0);
+        st.DST[idx] = axpy(st.Y[idx], k[s], st.dt);
+      } else {
+        const double w = EXACT ? x_add(st.ACC[idx], k[s]) : st.ACC[idx] + k[s];
+        const double yn = axpy(st.Y[idx], w, st.h6);
+        st.Y[idx] = yn;
+        bad |= hi_nonfinite(abs_hi(yn));
+      }
+    }
+  return bad;
+}
+
+// The dense fallback of the structured kernels, kept out of line so that its 64-entry matrix does not
+// raise the register count of the hot path (it reloads the cell from shared memory itself).
+template <int N>
+__device__ __noinline__ bool cold_cell(const SpeciesConst* sc, double fe, double cg, const double* SRC,
+                                       const double* inlet_row, uint32_t cc, bool write, StageCtx st) {
+  double c[N], up[N], k[N];
+#pragma unroll
+  for (int s = 0; s < N; ++s) {
+    c[s] = SRC[(size_t)s * st.nz + cc];
+    up[s] = (cc > 0) ? SRC[(size_t)s * st.nz + cc - 1] : inlet_row[s];
+  }
+  fast_row<N>(sc, fe, cg, c, up, k);  // warp-synchronous inside (pivot votes): called by whole warps
+  return write ? apply_stage<N, false>(st, cc, k, N) : false;
+}
+
+// ---- kernel ---------------------------------------------------------------------------------------
+// ARITH: CHROM_ARITH_FAST (dense register LU, N <= 8), CHROM_ARITH_EXACT, CHROM_KARITH_STRUCT.
+// N == 0: runtime n = b.n_species (9 .. kNMax); EXACT and STRUCT only.
+constexpr int multi_max_threads(int N, int ARITH) {
+  return (ARITH == CHROM_KARITH_STRUCT && N > 0) ? 512 : ((N > 0 && N <= 2) ? 512 : 256);
+}
+
+template <int N, int METHOD, int ARITH>
+__global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_resident(const BatchDev b, double* scratch) {
   constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
+  constexpr bool EXACT = (ARITH == CHROM_ARITH_EXACT);
+  constexpr int CAP = N > 0 ? N : kNMax;
   extern __shared__ double smem[];
+  const int n = N > 0 ? N : (int)b.n_species;
   const uint32_t nz = b.nz;
-  const uint32_t col = blockIdx.x;
   const int T = blockDim.x;
   const int tid = threadIdx.x;
-  const size_t plane = (size_t)N * nz;  // doubles per state array
+  const size_t plane = (size_t)n * nz;  // doubles per state array
   double* Y = smem;
   double* ACC = Y + plane;
   double* U0 = ACC + plane;
   double* U1 = U0 + plane;
-  double* inlet = U1 + plane;                              // [3][N] current step's inlet values
-  double* summ = inlet + 3 * N;                            // [N][5]: area, moment, max, tmax, v_prev
-  SpeciesConst* sc = (SpeciesConst*)(summ + 5 * N);        // [N]
-  __shared__ const double* tabs[N];
-
-  const chrom_multi_col cp = b.mcols[col];
-  const double fe = cp.fe, ue = cp.ue, dz = cp.dz;
-  const double cg = -ue / dz;  // FAST only
-  if (tid < N) {
-    const chrom_species sp = b.species[cp.species_off + tid];
-    SpeciesConst s;
-    s.lambda = sp.lambda;
-    s.K = sp.langmuir_k;
-    s.nbar = EXACT ? x_mul(cp.stationary_fraction, (double)sp.port_number)
-                   : cp.stationary_fraction * (double)sp.port_number;
-    s.a0 = 1.0 + fe * sp.lambda;
-    s.feNK = fe * (s.nbar * sp.langmuir_k);
-    sc[tid] = s;
-    tabs[tid] = b.tables + (size_t)sp.inj_table * b.steps * ST;
-  }
-  for (size_t i = tid; i < plane; i += T) {
-    Y[i] = b.y0 ? b.y0[(size_t)col * plane + i] : 0.0;
-    ACC[i] = 0.0;
-  }
-  __syncthreads();
+  double* inlet = U1 + plane;                        // [3][n] current step's inlet values
+  double* summ = inlet + 3 * n;                      // [n][5]: area, moment, max, tmax, v_prev
+  SpeciesConst* sc = (SpeciesConst*)(summ + 5 * n);  // [n]
+  __shared__ const double* tabs[CAP];
+  // per-thread scratch (runtime-n dense paths): element e of this thread at my_scratch[e * sstride]
+  const size_t sstride = (size_t)gridDim.x * T;
+  double* my_scratch = scratch ? scratch + (size_t)blockIdx.x * T + tid : nullptr;
 
   const double dt = b.dt, h2 = b.half_dt, h6 = b.sixth_dt;
   const uint32_t steps = b.steps;
   const int cpt = (int)((nz + T - 1) / T);  // cells per thread
-  const bool out_thread = ((int)((nz - 1) % T) == tid);
-
   auto axpy = [](double y, double k, double h) { return EXACT ? x_add(y, x_mul(k, h)) : fma(k, h, y); };
 
-  // initial samples
-  if (b.outlet && tid < N) b.outlet[((size_t)col * N + tid) * b.n_out] = Y[(size_t)tid * nz + nz - 1];
-  if (b.snapshots)
-    for (size_t i = tid; i < plane; i += T) b.snapshots[(size_t)col * b.n_snap * plane + i] = Y[i];
-  if (tid < N) {
-    const double v0 = Y[(size_t)tid * nz + nz - 1];
-    summ[tid * 5 + 0] = 0.0;
-    summ[tid * 5 + 1] = 0.0;
-    summ[tid * 5 + 2] = v0;
-    summ[tid * 5 + 3] = 0.0;
-    summ[tid * 5 + 4] = v0;
-  }
-  uint32_t out_count = b.outlet_stride, snap_count = b.snapshot_stride, out_slot = 1, snap_slot = 1;
-  bool done = false;
-
-  // One stage: K = f(SRC, inlet row `irow`), then the stage algebra selected by `stage`.
-  auto run_stage = [&](const double* SRC, double* DST, int irow, int stage) -> bool {
-    bool bad = false;
-    for (int ci = 0; ci < cpt; ++ci) {
-      const uint32_t cell = (uint32_t)tid + (uint32_t)ci * T;
-      const bool live = cell < nz;
-      const uint32_t cc = live ? cell : nz - 1;  // idle lanes recompute the last cell, never store
-      double c[N], up[N], k[N];
-#pragma unroll
-      for (int s = 0; s < N; ++s) {
-        c[s] = SRC[(size_t)s * nz + cc];
-        up[s] = (cc > 0) ? SRC[(size_t)s * nz + cc - 1] : inlet[irow * N + s];
-      }
-      if (EXACT) exact_row<N>(sc, fe, ue, dz, c, up, k);
-      else fast_row<N>(sc, fe, cg, c, up, k);
-      if (!live) continue;
-#pragma unroll
-      for (int s = 0; s < N; ++s) {
-        const size_t idx = (size_t)s * nz + cc;
-        if (METHOD == CHROM_EULER) {
-          const double yn = axpy(Y[idx], k[s], dt);
-          Y[idx] = yn;  // Euler reads SRC = U0 (copy of Y), so Y can be overwritten
-          DST[idx] = yn;
-          bad |= hi_nonfinite(abs_hi(yn));
-        } else if (stage == 1) {
-          ACC[idx] = k[s];
-          DST[idx] = axpy(Y[idx], k[s], h2);
-        } else if (stage == 2) {
-          ACC[idx] = axpy(ACC[idx], k[s], 2.0);
-          DST[idx] = axpy(Y[idx], k[s], h2);
-        } else if (stage == 3) {
-          ACC[idx] = axpy(ACC[idx], k[s], 2.0);
-          DST[idx] = axpy(Y[idx], k[s], dt);
-        } else {
-          const double w = EXACT ? x_add(ACC[idx], k[s]) : ACC[idx] + k[s];
-          const double yn = axpy(Y[idx], w, h6);
-          Y[idx] = yn;
-          bad |= hi_nonfinite(abs_hi(yn));
-        }
-      }
+  for (uint32_t col = blockIdx.x; col < b.n_cols; col += gridDim.x) {  // persistent CTAs over columns
+    const chrom_multi_col cp = b.mcols[col];
+    const double fe = cp.fe, ue = cp.ue, dz = cp.dz;
+    const double cg = -ue / dz;  // FAST only
+    __syncthreads();             // the previous column's readers of sc / tabs / Y are done
+    for (int s = tid; s < n; s += T) {
+      const chrom_species sp = b.species[cp.species_off + s];
+      SpeciesConst q;
+      q.lambda = sp.lambda;
+      q.K = sp.langmuir_k;
+      q.nbar = EXACT ? x_mul(cp.stationary_fraction, (double)sp.port_number)
+                     : cp.stationary_fraction * (double)sp.port_number;
+      q.a0 = 1.0 + fe * sp.lambda;
+      q.feNK = fe * (q.nbar * sp.langmuir_k);
+      q.feNK2 = q.feNK;
+      sc[s] = q;
+      tabs[s] = b.tables + (size_t)sp.inj_table * b.steps * ST;
     }
-    return bad;
-  };
-
-  if (METHOD == CHROM_EULER) {
-    for (size_t i = tid; i < plane; i += T) U0[i] = Y[i];
-  }
-
-  for (uint32_t step = 0; step < steps; ++step) {
-    if (tid < N * ST) {  // inlet values of this step: [stage row][species]
-      const int s = tid % N, r = tid / N;
-      inlet[r * N + s] = tabs[s][(size_t)step * ST + r];
+    for (size_t i = tid; i < plane; i += T) {
+      Y[i] = b.y0 ? b.y0[(size_t)col * plane + i] : 0.0;
+      ACC[i] = 0.0;
     }
     __syncthreads();
-    bool bad;
-    if (METHOD == CHROM_RK4) {
-      run_stage(Y, U0, 0, 1);
-      __syncthreads();
-      run_stage(U0, U1, 1, 2);
-      __syncthreads();
-      run_stage(U1, U0, 1, 3);
-      __syncthreads();
-      bad = run_stage(U0, nullptr, 2, 4);
-    } else {
-      // ping-pong: even steps read U0 / write U1, odd steps the reverse; Y always holds the new state
-      bad = (step & 1u) ? run_stage(U1, U0, 0, 0) : run_stage(U0, U1, 0, 0);
-    }
-    const int any_bad = __syncthreads_or(bad);
 
-    // ---- samples ----------------------------------------------------------------------------
-    if (tid < N) {
-      const double v = Y[(size_t)tid * nz + nz - 1];
-      if (b.outlet && --out_count == 0) {
-        out_count = b.outlet_stride;
-        b.outlet[((size_t)col * N + tid) * b.n_out + out_slot] = v;
-        ++out_slot;
-      }
-      if (b.summary) {
-        const double t0 = (double)step * dt, t1 = ((double)step + 1.0) * dt;
-        const double w = 0.5 * (t1 - t0);
-        double* sm = summ + tid * 5;
-        sm[0] = fma(w, sm[4] + v, sm[0]);
-        sm[1] = fma(w, fma(t0, sm[4], t1 * v), sm[1]);
-        if (v > sm[2]) {
-          sm[2] = v;
-          sm[3] = t1;
+    // initial samples
+    for (int s = tid; s < n; s += T) {
+      const double v0 = Y[(size_t)s * nz + nz - 1];
+      if (b.outlet) b.outlet[((size_t)col * n + s) * b.n_out] = v0;
+      summ[s * 5 + 0] = 0.0;
+      summ[s * 5 + 1] = 0.0;
+      summ[s * 5 + 2] = v0;
+      summ[s * 5 + 3] = 0.0;
+      summ[s * 5 + 4] = v0;
+    }
+    if (b.snapshots)
+      for (size_t i = tid; i < plane; i += T) b.snapshots[(size_t)col * b.n_snap * plane + i] = Y[i];
+    uint32_t out_count = b.outlet_stride, snap_count = b.snapshot_stride, out_slot = 1, snap_slot = 1;
+    bool done = false;
+
+    // One stage: K = f(SRC, inlet row `irow`), then the stage algebra selected by `stage`.
+    auto run_stage = [&](const double* SRC, double* DST, int irow, int stage) -> bool {
+      bool bad = false;
+      StageCtx st{Y, ACC, DST, nz, METHOD == CHROM_EULER ? 0 : stage, dt, h2, h6};
+      unsigned redo_mask = 0u;  // structured kernels: cells whose LU needs a row exchange
+      for (int ci = 0; ci < cpt; ++ci) {
+        const uint32_t cell = (uint32_t)tid + (uint32_t)ci * T;
+        const bool live = cell < nz;
+        const uint32_t cc = live ? cell : nz - 1;  // idle lanes recompute the last cell, never store
+        double k[CAP];
+        if constexpr (ARITH == CHROM_KARITH_STRUCT && N > 0) {
+          const bool redo = structured_cell<N>(sc, cg, SRC, inlet + irow * n, nz, cc, k);
+          if (redo) redo_mask |= 1u << ci;
+          else if (live) bad |= apply_stage<N, false>(st, cc, k, n);
+        } else {
+          double c[CAP], up[CAP];
+#pragma unroll
+          for (int s = 0; s < CAP; ++s)
+            if (s < n) {
+              c[s] = SRC[(size_t)s * nz + cc];
+              up[s] = (cc > 0) ? SRC[(size_t)s * nz + cc - 1] : inlet[irow * n + s];
+            }
+          if constexpr (EXACT) {
+            if constexpr (N > 0) exact_row<N>(sc, fe, ue, dz, c, up, k);
+            else exact_row_scratch(n, sc, fe, ue, dz, c, up, k, my_scratch, sstride);
+          } else if constexpr (ARITH == CHROM_KARITH_STRUCT) {
+            if (structured_row<0>(n, sc, cg, c, up, k)) dense_row_scratch(n, sc, cg, c, up, k, my_scratch, sstride);
+          } else {
+            fast_row<(N > 0 ? N : 1)>(sc, fe, cg, c, up, k);
+          }
+          if (live) bad |= apply_stage<N, EXACT>(st, cc, k, n);
         }
-        sm[4] = v;
+      }
+      if constexpr (ARITH == CHROM_KARITH_STRUCT && N > 0) {
+        // cold pass: redo the flagged cells with the dense row-exchanging LU (whole warps, out of line)
+        if (__any_sync(0xffffffffu, redo_mask != 0u)) {
+          for (int ci = 0; ci < cpt; ++ci) {
+            const bool mine = (redo_mask >> ci) & 1u;
+            if (!__any_sync(0xffffffffu, mine)) continue;
+            const uint32_t cell = (uint32_t)tid + (uint32_t)ci * T;
+            const bool live = cell < nz;
+            bad |= cold_cell<(N > 0 ? N : 1)>(sc, fe, cg, SRC, inlet + irow * n, live ? cell : nz - 1, mine && live, st);
+          }
+        }
+      }
+      return bad;
+    };
+
+    if (METHOD == CHROM_EULER) {
+      for (size_t i = tid; i < plane; i += T) U0[i] = Y[i];
+    }
+
+    for (uint32_t step = 0; step < steps; ++step) {
+      for (int i = tid; i < n * ST; i += T) {  // inlet values of this step: [stage row][species]
+        const int s = i % n, r = i / n;
+        inlet[r * n + s] = tabs[s][(size_t)step * ST + r];
+      }
+      __syncthreads();
+      bool bad;
+      if (METHOD == CHROM_RK4) {
+        run_stage(Y, U0, 0, 1);
+        __syncthreads();
+        run_stage(U0, U1, 1, 2);
+        __syncthreads();
+        run_stage(U1, U0, 1, 3);
+        __syncthreads();
+        bad = run_stage(U0, nullptr, 2, 4);
+      } else {
+        // ping-pong: even steps read U0 / write U1, odd steps the reverse; Y always holds the new state
+        bad = (step & 1u) ? run_stage(U1, U0, 0, 0) : run_stage(U0, U1, 0, 0);
+      }
+      const int any_bad = __syncthreads_or(bad);
+
+      // ---- samples --------------------------------------------------------------------------
+      const bool out_now = b.outlet && (--out_count == 0);
+      if (out_now) out_count = b.outlet_stride;
+      for (int s = tid; s < n; s += T) {
+        const double v = Y[(size_t)s * nz + nz - 1];
+        if (out_now) b.outlet[((size_t)col * n + s) * b.n_out + out_slot] = v;
+        if (b.summary) {
+          const double t0 = (double)step * dt, t1 = ((double)step + 1.0) * dt;
+          const double w = 0.5 * (t1 - t0);
+          double* sm = summ + s * 5;
+          sm[0] = fma(w, sm[4] + v, sm[0]);
+          sm[1] = fma(w, fma(t0, sm[4], t1 * v), sm[1]);
+          if (v > sm[2]) {
+            sm[2] = v;
+            sm[3] = t1;
+          }
+          sm[4] = v;
+        }
+      }
+      if (out_now) ++out_slot;
+      if (b.snapshots && --snap_count == 0) {
+        snap_count = b.snapshot_stride;
+        double* dst = b.snapshots + ((size_t)col * b.n_snap + snap_slot) * plane;
+        for (size_t i = tid; i < plane; i += T) dst[i] = Y[i];
+        ++snap_slot;
+      }
+      if (any_bad && !done) {  // validate_state: NaN anywhere wins over Inf (solver/mod.rs:519-548)
+        bool has_nan = false;
+        for (size_t i = tid; i < plane; i += T) has_nan |= (Y[i] != Y[i]);
+        const int any_nan = __syncthreads_or(has_nan);
+        if (tid == 0 && b.status) b.status[col] = any_nan ? (long long)(step + 1) : -(long long)(step + 1);
+        done = true;
       }
     }
-    if (b.snapshots && --snap_count == 0) {
-      snap_count = b.snapshot_stride;
-      double* dst = b.snapshots + ((size_t)col * b.n_snap + snap_slot) * plane;
-      for (size_t i = tid; i < plane; i += T) dst[i] = Y[i];
-      ++snap_slot;
-    }
-    if (any_bad && !done) {  // validate_state: NaN anywhere wins over Inf (solver/mod.rs:519-548)
-      bool has_nan = false;
-      for (size_t i = tid; i < plane; i += T) has_nan |= (Y[i] != Y[i]);
-      const int any_nan = __syncthreads_or(has_nan);
-      if (tid == 0 && b.status) b.status[col] = any_nan ? (long long)(step + 1) : -(long long)(step + 1);
-      done = true;
-    }
-  }
-  (void)out_thread;
-  __syncthreads();
-  if (b.final_state)
-    for (size_t i = tid; i < plane; i += T) b.final_state[(size_t)col * plane + i] = Y[i];
-  if (b.summary && tid < N) {
-    double* s = b.summary + ((size_t)col * N + tid) * 4;
-    const double* sm = summ + tid * 5;
-    s[0] = sm[0];
-    s[1] = (sm[0] != 0.0) ? sm[1] / sm[0] : 0.0;
-    s[2] = sm[2];
-    s[3] = sm[3];
+    __syncthreads();
+    if (b.final_state)
+      for (size_t i = tid; i < plane; i += T) b.final_state[(size_t)col * plane + i] = Y[i];
+    if (b.summary)
+      for (int s = tid; s < n; s += T) {
+        double* o = b.summary + ((size_t)col * n + s) * 4;
+        const double* sm = summ + s * 5;
+        o[0] = sm[0];
+        o[1] = (sm[0] != 0.0) ? sm[1] / sm[0] : 0.0;
+        o[2] = sm[2];
+        o[3] = sm[3];
+      }
   }
 }
 
-typedef void (*mkern_t)(const BatchDev);
+typedef void (*mkern_t)(const BatchDev, double*);
 
 template <int N>
 mkern_t pick_n(int method, int arith) {
-  if (method == CHROM_RK4)
-    return arith == CHROM_ARITH_EXACT ? k_multi_resident<N, CHROM_RK4, true> : k_multi_resident<N, CHROM_RK4, false>;
-  return arith == CHROM_ARITH_EXACT ? k_multi_resident<N, CHROM_EULER, true> : k_multi_resident<N, CHROM_EULER, false>;
+  if (method == CHROM_RK4) {
+    if (arith == CHROM_ARITH_EXACT) return k_multi_resident<N, CHROM_RK4, CHROM_ARITH_EXACT>;
+    if (arith == CHROM_KARITH_STRUCT) return k_multi_resident<N, CHROM_RK4, CHROM_KARITH_STRUCT>;
+    return N > 0 ? k_multi_resident<(N > 0 ? N : 1), CHROM_RK4, CHROM_ARITH_FAST> : nullptr;
+  }
+  if (arith == CHROM_ARITH_EXACT) return k_multi_resident<N, CHROM_EULER, CHROM_ARITH_EXACT>;
+  if (arith == CHROM_KARITH_STRUCT) return k_multi_resident<N, CHROM_EULER, CHROM_KARITH_STRUCT>;
+  return N > 0 ? k_multi_resident<(N > 0 ? N : 1), CHROM_EULER, CHROM_ARITH_FAST> : nullptr;
 }
 
 mkern_t lookup_multi(int n, int method, int arith) {
@@ -512,7 +872,7 @@ mkern_t lookup_multi(int n, int method, int arith) {
     case 7: return pick_n<7>(method, arith);
     case 8: return pick_n<8>(method, arith);
   }
-  return nullptr;
+  return (n >= 9 && n <= kNMax) ? pick_n<0>(method, arith) : nullptr;
 }
 
 size_t multi_smem_bytes(int n, uint32_t nz) {
@@ -521,10 +881,25 @@ size_t multi_smem_bytes(int n, uint32_t nz) {
 
 }  // namespace
 
+// Resolves the kernel arithmetic of a multi-species batch: n > 8 has no register LU, so FAST maps to
+// the structured elimination there; CHROM_MULTI_STRUCT=1 opts n <= 8 into it as well.
+int multi_kernel_arith(int n, int arith) {
+  if (arith == CHROM_ARITH_EXACT) return arith;
+  if (arith == CHROM_KARITH_STRUCT || n > 8) return CHROM_KARITH_STRUCT;
+  const char* e = getenv("CHROM_MULTI_STRUCT");
+  return (e && atoi(e) != 0) ? CHROM_KARITH_STRUCT : CHROM_ARITH_FAST;
+}
+
+// doubles of per-thread scratch the chosen kernel needs (0 for the register-only variants)
+size_t multi_scratch_per_thread(int n, int karith) {
+  if (n <= 8) return 0;
+  return karith == CHROM_ARITH_EXACT ? (size_t)3 * n * n : (size_t)n * n;
+}
+
 bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why) {
   const int n = (int)b.n_species;
-  if (n < 1 || n > 8) {
-    if (why) *why = "n_species outside 1..8 (per-thread register LU); the warp-per-cell path is not built yet";
+  if (n < 1 || n > kNMax) {
+    if (why) *why = "n_species outside 1..64";
     return false;
   }
   const size_t smem = multi_smem_bytes(n, b.nz);
@@ -532,28 +907,33 @@ bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::
     if (why) *why = "nz * n_species exceeds the shared-memory-resident capacity (4*n*nz doubles <= 227 KB)";
     return false;
   }
-  const int tmax = multi_max_threads(n);
+  const int karith = b.arith;  // already resolved by multi_kernel_arith
+  const int tmax = n <= 8 ? multi_max_threads(n, karith) : 256;
   int T = (int)std::min<uint32_t>((b.nz + 31u) / 32u * 32u, (uint32_t)tmax);
   // balance: fewest threads that keep the same number of cells per thread
   const int cpt = (int)((b.nz + T - 1) / T);
   T = (int)(((b.nz + cpt - 1) / cpt + 31u) / 32u * 32u);
+  int ctas_per_sm;
+  {
+    const int regs = (n > 8) ? 255 : (karith == CHROM_KARITH_STRUCT ? 128 : (n >= 8 ? 232 : (n >= 5 ? 200 : 128)));
+    const int by_smem = (int)((227u * 1024u) / (smem + 1024));
+    const int by_regs = 65536 / (T * regs);
+    ctas_per_sm = std::max(1, std::min(by_smem, by_regs));
+  }
   g->kind = 4;
   g->M = cpt;
   g->L = T;
   g->cpw = 1;
   g->warps_per_col = T / 32;
   g->block = dim3(T);
-  g->grid = dim3(b.n_cols);
+  g->cols_per_wave = (uint32_t)(sm_count * ctas_per_sm);
+  g->grid = dim3(std::min<uint32_t>(b.n_cols, g->cols_per_wave));
   g->smem = smem;
-  {
-    const int by_smem = (int)((227u * 1024u) / (smem + 1024));
-    const int by_regs = 65536 / (T * (n >= 8 ? 232 : (n >= 5 ? 200 : 128)));
-    g->cols_per_wave = (uint32_t)(sm_count * std::max(1, std::min(by_smem, by_regs)));
-  }
-  char buf[200];
-  snprintf(buf, sizeof buf, "multi_resident<n=%d,%s,%s> threads/col=%d cells/thread=%d smem=%zuB grid=%u", n,
-           b.method == CHROM_RK4 ? "RK4" : "Euler", b.arith == CHROM_ARITH_EXACT ? "exact" : "fast", T, cpt, smem,
-           b.n_cols);
+  char buf[240];
+  snprintf(buf, sizeof buf, "multi_resident<n=%d%s,%s,%s> threads/col=%d cells/thread=%d smem=%zuB persistent grid=%u", n,
+           n > 8 ? "(runtime)" : "", b.method == CHROM_RK4 ? "RK4" : "Euler",
+           karith == CHROM_ARITH_EXACT ? "exact" : (karith == CHROM_KARITH_STRUCT ? "fast-structured-LU" : "fast-dense-LU"),
+           T, cpt, smem, g->grid.x);
   g->name = buf;
   return true;
 }
@@ -563,7 +943,8 @@ cudaError_t multi_resident_launch(const BatchDev& b, const LaunchGeom& g, cudaSt
   if (!k) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return e;
-  k<<<dim3(b.n_cols), g.block, g.smem, s>>>(b);
+  const uint32_t grid = std::min<uint32_t>(b.n_cols, g.cols_per_wave ? g.cols_per_wave : b.n_cols);
+  k<<<dim3(grid), g.block, g.smem, s>>>(b, b.scratch);
   return cudaGetLastError();
 }
 

@@ -47,6 +47,11 @@ extern "C" {
  *         to the reference arithmetic (n<=4 closed-form inverses and n>=5 nalgebra LU included). */
 #define CHROM_ARITH_FAST 0
 #define CHROM_ARITH_EXACT 1
+/* LangmuirMulti only: FAST arithmetic with the LU of I + Fe*M = diag(alpha) - p q^T carried out on
+ * the O(n) scalars that define it (same pivots, same partial-pivoting test; a cell that needs a row
+ * exchange is redone with the dense LU).  The default FAST mode uses the dense register LU for
+ * n <= 8 and this mode for n > 8. */
+#define CHROM_ARITH_FAST_STRUCTURED 3
 
 #define CHROM_INJ_NONE 0
 #define CHROM_INJ_DIRAC 1     /* p0 = time, p1 = amount */

@@ -102,7 +102,29 @@ def test_species_counts_exact_and_fast(ctx, n, nz):
     assert r.status[0] == 0 and ref.n_singular == 0
     assert_bit_equal(r.snapshots[0].transpose(0, 2, 1), ref.trajectory[::40], f"n={n} nz={nz} snapshots")
     assert_bit_equal(r.outlet[0], ref.outlet, f"n={n} nz={nz} outlet")
-    f = run_gpu(ctx, [m], cb.RK4, T, steps, cb.ARITH_FAST, y0=y0_dev)
+    for arith in (cb.ARITH_FAST, cb.ARITH_FAST_STRUCTURED):
+        f = run_gpu(ctx, [m], cb.RK4, T, steps, arith, y0=y0_dev)
+        assert max_rel_err(f.final_state[0].T, ref.final_state) <= PROFILE_RTOL
+        assert max_rel_err(f.outlet[0], ref.outlet) <= PROFILE_RTOL
+
+
+@pytest.mark.parametrize("n", [9, 12, 16, 24, 40])
+@pytest.mark.parametrize("method", [cb.RK4, cb.EULER], ids=["rk4", "euler"])
+def test_many_species_runtime_n(ctx, n, method):
+    """n > 8: runtime-n kernels.  EXACT = nalgebra LU restated on per-thread scratch matrices (bit-identical),
+    FAST = structured LU in O(n) scalars (dense pivoted LU on scratch when a row exchange is needed)."""
+    nz, steps, T = 40, 60, 6.0
+    rng = np.random.default_rng(1000 + n)
+    y0 = rng.uniform(0.0, 0.05, size=(nz, n))
+    m = cb.LangmuirMulti.new(random_species(n, seed=n), nz, 0.4, 1e-3, 0.1)
+    ref = O.solve_multi(to_oracle(m), method, T, steps, y0=y0, want_trajectory=True)
+    y0_dev = np.ascontiguousarray(y0.T)[None]
+    r = run_gpu(ctx, [m, m], method, T, steps, cb.ARITH_EXACT, y0=np.concatenate([y0_dev, y0_dev]), snapshot_stride=20)
+    assert not r.status.any() and ref.n_singular == 0
+    for c in range(2):
+        assert_bit_equal(r.snapshots[c].transpose(0, 2, 1), ref.trajectory[::20], f"n={n} snapshots col {c}")
+        assert_bit_equal(r.outlet[c], ref.outlet, f"n={n} outlet col {c}")
+    f = run_gpu(ctx, [m], method, T, steps, cb.ARITH_FAST, y0=y0_dev)
     assert max_rel_err(f.final_state[0].T, ref.final_state) <= PROFILE_RTOL
     assert max_rel_err(f.outlet[0], ref.outlet) <= PROFILE_RTOL
 
@@ -125,7 +147,7 @@ def pivoting_case(n):
     return m, y0
 
 
-@pytest.mark.parametrize("n", [2, 3, 5, 8])
+@pytest.mark.parametrize("n", [2, 3, 5, 8, 12])
 def test_partial_pivoting_is_exercised(ctx, n):
     """The LU must pivot (premise asserted on the first cell's matrix).  EXACT stays bit-identical
     (nalgebra's row exchanges restated), FAST (compare-and-swap pivoting) within tolerance."""
@@ -139,8 +161,9 @@ def test_partial_pivoting_is_exercised(ctx, n):
     r = run_gpu(ctx, [m], cb.RK4, T, steps, cb.ARITH_EXACT, y0=y0_dev)
     assert r.status[0] == 0 and ref.status == 0
     assert_bit_equal(r.final_state[0].T, ref.final_state, f"n={n} pivoting, exact")
-    f = run_gpu(ctx, [m], cb.RK4, T, steps, cb.ARITH_FAST, y0=y0_dev)
-    assert max_rel_err(f.final_state[0].T, ref.final_state) <= PROFILE_RTOL
+    for arith in (cb.ARITH_FAST, cb.ARITH_FAST_STRUCTURED):  # structured: pivot test fires -> dense redo
+        f = run_gpu(ctx, [m], cb.RK4, T, steps, arith, y0=y0_dev)
+        assert max_rel_err(f.final_state[0].T, ref.final_state) <= PROFILE_RTOL
 
 
 def test_c5_shaped_batch(ctx):
@@ -152,8 +175,14 @@ def test_c5_shaped_batch(ctx):
     assert not r.status.any() and not ost.any()
     assert_bit_equal(r.final_state, of, "final")
     assert_bit_equal(r.outlet, oo, "outlet")
-    f = run_gpu(ctx, models, cb.RK4, T, steps, cb.ARITH_FAST)
-    assert max_rel_err(f.final_state, of) <= PROFILE_RTOL
+    for arith in (cb.ARITH_FAST, cb.ARITH_FAST_STRUCTURED):
+        f = run_gpu(ctx, models, cb.RK4, T, steps, arith)
+        assert max_rel_err(f.final_state, of) <= PROFILE_RTOL
+    many = W.multi_batch_models(700, 8, 64, seed=3)  # more columns than persistent CTAs: the column loop
+    T2 = 600.0 * 10 / 4096
+    oo, of, ost = O.solve_multi_batch([to_oracle(m) for m in many], O.RK4, T2, 10)
+    r = run_gpu(ctx, many, cb.RK4, T2, 10, cb.ARITH_EXACT)
+    assert_bit_equal(r.final_state, of, "700 columns, persistent CTAs")
 
 
 def test_interior_zero_on_empty_column(ctx):
