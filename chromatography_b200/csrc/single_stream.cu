@@ -12,7 +12,9 @@
 // at M = 8, no inter-CTA communication.  Tile 0 starts at the inlet and keeps everything.
 // Algorithmic HBM traffic: 16 B per cell-step (read y_n, write y_n+1); both ping-pong buffers of
 // the 2^22 column (67 MB) fit the 126 MB L2.
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "arith.cuh"
 #include "kernels.h"
@@ -25,15 +27,19 @@ constexpr int kM = 8;           // cells per lane
 constexpr int kTile = 32 * kM;  // cells per warp tile
 constexpr int kWarps = 4;       // warps per CTA
 
-// status word while streaming: 0 = clean, else (step << 1) | has_nan; atomicMax keeps NaN over Inf
-// within a step, later steps never overwrite (solver/mod.rs:519-548: NaN wins, first step wins).
-template <int METHOD, int ARITH>
+// status word while streaming: ~0 = clean, else (step << 1) | (NaN ? 0 : 1), merged with atomicMin: the first
+// bad step wins, NaN over Inf within it (solver/mod.rs:519-548).
+//
+// FUSE consecutive time steps are advanced per launch (temporal blocking): the state crosses HBM/L2
+// once per FUSE steps, the halo grows to 4*FUSE cells (FUSE = 4: 6.5 % redundant work at M = 8).
+// Outlet samples and the non-finite scan are taken after every sub-step, on cells no halo touches.
+template <int METHOD, int ARITH, int FUSE>
 __global__ void __launch_bounds__(kWarps * 32)
     k_single_stream_step(const BatchDev b, const double* __restrict__ src, double* __restrict__ dst, uint32_t step,
-                         unsigned long long* __restrict__ code, int out_slot, int tiles_per_col) {
+                         unsigned long long* __restrict__ code, int nsub, int tiles_per_col) {
   constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
-  constexpr int H = (METHOD == CHROM_RK4) ? 4 : 0;  // RK4 stage values reach 4 cells upstream
-  constexpr int V = kTile - H;  // cells a non-first tile contributes
+  constexpr int H = (METHOD == CHROM_RK4) ? 4 * FUSE : 0;  // RK4 stage values reach 4 cells upstream per step
+  constexpr int V = kTile - H;                             // cells a non-first tile contributes
   using Q = Coef<ARITH>;
   const int lane = threadIdx.x & 31;
   const int tile = (int)(blockIdx.x * kWarps + (threadIdx.x >> 5));
@@ -46,15 +52,13 @@ __global__ void __launch_bounds__(kWarps * 32)
   // stale register in the Euler/fast variant; found by the parity tests).
   const long long base = (long long)tile * V;
   const long long cell0 = base + (long long)lane * kM;
-  const int first_valid = (tile == 0) ? 0 : H;  // tile-local index of the first cell this tile stores
+  const int first_valid = (tile == 0) ? 0 : H;  // tile-local index of the first cell this tile owns
+  const int local0 = lane * kM;                 // tile-local index of this lane's first cell
 
   const chrom_single_col cp = b.scols[col];
   Q q;
   q.init(cp);
   const double* __restrict__ tab = b.tables + ((size_t)cp.inj_table * b.steps + step) * ST;
-  const double cin0 = tab[0];
-  const double cin1 = (ST == 3) ? tab[1] : 0.0;
-  const double cin2 = (ST == 3) ? tab[2] : 0.0;
   const double dt = b.dt, h2 = b.half_dt, h6 = b.sixth_dt;
 
   const double* __restrict__ s = src + (size_t)col * nz;
@@ -74,83 +78,101 @@ __global__ void __launch_bounds__(kWarps * 32)
     for (int j = 0; j < kM; ++j) y[j] = (cell0 + j < (long long)nz) ? s[cell0 + j] : 0.0;
   }
   const bool inlet_lane = (tile == 0) && (lane == 0);
+  double euler_up = 0.0;  // Euler (never fused): the upstream neighbour of the tile's first cell is an input
+  if (METHOD == CHROM_EULER && lane == 0 && tile > 0) euler_up = s[cell0 - 1];
 
   auto exchange = [&](double last, double inlet) -> double {
     const double up = __shfl_up_sync(0xffffffffu, last, 1);
     return inlet_lane ? inlet : up;  // lane 0 of a later tile gets its own value back: halo, discarded
   };
 
-  if (METHOD == CHROM_RK4) {
-    double up = exchange(y[kM - 1], cin0);
-#pragma unroll
-    for (int j = kM - 1; j >= 0; --j) {
-      const double k = q.rhs(y[j], j > 0 ? y[j - 1] : up);
-      acc[j] = k;
-      u[j] = Q::axpy(y[j], k, h2);
-    }
-    up = exchange(u[kM - 1], cin1);
-#pragma unroll
-    for (int j = kM - 1; j >= 0; --j) {
-      const double k = q.rhs(u[j], j > 0 ? u[j - 1] : up);
-      acc[j] = Q::axpy(acc[j], k, 2.0);
-      u[j] = Q::axpy(y[j], k, h2);
-    }
-    up = exchange(u[kM - 1], cin1);
-#pragma unroll
-    for (int j = kM - 1; j >= 0; --j) {
-      const double k = q.rhs(u[j], j > 0 ? u[j - 1] : up);
-      acc[j] = Q::axpy(acc[j], k, 2.0);
-      u[j] = Q::axpy(y[j], k, dt);
-    }
-    up = exchange(u[kM - 1], cin2);
-#pragma unroll
-    for (int j = kM - 1; j >= 0; --j) {
-      const double k = q.rhs(u[j], j > 0 ? u[j - 1] : up);
-      y[j] = Q::axpy(y[j], Q::add(acc[j], k), h6);
-    }
-  } else {
-    // Euler: the upstream neighbour of the tile's first cell is an input, read it directly
-    double up = exchange(y[kM - 1], cin0);
-    if (lane == 0 && tile > 0) up = s[cell0 - 1];
-#pragma unroll
-    for (int j = kM - 1; j >= 0; --j) {
-      const double k = q.rhs(y[j], j > 0 ? y[j - 1] : up);
-      y[j] = Q::axpy(y[j], k, dt);
-    }
-  }
-
-  // ---- store the valid cells, outlet sample, non-finite scan ---------------------------------------
-  const int local0 = lane * kM;  // tile-local index of this lane's first cell
   bool bad = false, has_nan = false;
-  if (vec && local0 >= first_valid) {
-    double2* dv = reinterpret_cast<double2*>(d + cell0);
+  uint32_t bad_step = 0;
+  for (int f = 0; f < FUSE; ++f) {
+    if (f >= nsub) break;
+    const double cin0 = tab[f * ST];
+    const double cin1 = (ST == 3) ? tab[f * ST + 1] : 0.0;
+    const double cin2 = (ST == 3) ? tab[f * ST + 2] : 0.0;
+    if (METHOD == CHROM_RK4) {
+      double up = exchange(y[kM - 1], cin0);
 #pragma unroll
-    for (int j = 0; j < kM / 2; ++j) dv[j] = make_double2(y[2 * j], y[2 * j + 1]);
+      for (int j = kM - 1; j >= 0; --j) {
+        const double k = q.rhs(y[j], j > 0 ? y[j - 1] : up);
+        acc[j] = k;
+        u[j] = Q::axpy(y[j], k, h2);
+      }
+      up = exchange(u[kM - 1], cin1);
 #pragma unroll
-    for (int j = 0; j < kM; ++j) {
-      bad |= hi_nonfinite(abs_hi(y[j]));
-      has_nan |= (y[j] != y[j]);
+      for (int j = kM - 1; j >= 0; --j) {
+        const double k = q.rhs(u[j], j > 0 ? u[j - 1] : up);
+        acc[j] = Q::axpy(acc[j], k, 2.0);
+        u[j] = Q::axpy(y[j], k, h2);
+      }
+      up = exchange(u[kM - 1], cin1);
+#pragma unroll
+      for (int j = kM - 1; j >= 0; --j) {
+        const double k = q.rhs(u[j], j > 0 ? u[j - 1] : up);
+        acc[j] = Q::axpy(acc[j], k, 2.0);
+        u[j] = Q::axpy(y[j], k, dt);
+      }
+      up = exchange(u[kM - 1], cin2);
+#pragma unroll
+      for (int j = kM - 1; j >= 0; --j) {
+        const double k = q.rhs(u[j], j > 0 ? u[j - 1] : up);
+        y[j] = Q::axpy(y[j], Q::add(acc[j], k), h6);
+      }
+    } else {
+      double up = exchange(y[kM - 1], cin0);
+      if (lane == 0 && tile > 0) up = euler_up;
+#pragma unroll
+      for (int j = kM - 1; j >= 0; --j) {
+        const double k = q.rhs(y[j], j > 0 ? y[j - 1] : up);
+        y[j] = Q::axpy(y[j], k, dt);
+      }
     }
-    if (cell0 + kM == (long long)nz && out_slot >= 0) b.outlet[(size_t)col * b.n_out + out_slot] = y[kM - 1];
-  } else {
+    // ---- per sub-step: outlet sample and non-finite scan on the cells this tile owns ------------------
+    const uint32_t done_steps = step + (uint32_t)f + 1u;
+    const bool want_out = b.outlet && b.outlet_stride && (done_steps % b.outlet_stride == 0u);
+    bool sub_bad = false, sub_nan = false;
 #pragma unroll
     for (int j = 0; j < kM; ++j) {
       const long long cell = cell0 + j;
       if (local0 + j >= first_valid && cell < (long long)nz) {
-        d[cell] = y[j];
-        bad |= hi_nonfinite(abs_hi(y[j]));
-        has_nan |= (y[j] != y[j]);
-        if (cell == (long long)nz - 1 && out_slot >= 0) b.outlet[(size_t)col * b.n_out + out_slot] = y[j];
+        sub_bad |= hi_nonfinite(abs_hi(y[j]));
+        sub_nan |= (y[j] != y[j]);
+        if (want_out && cell == (long long)nz - 1)
+          b.outlet[(size_t)col * b.n_out + done_steps / b.outlet_stride] = y[j];
       }
+    }
+    if (sub_bad && !bad) {  // remember the FIRST bad sub-step of this lane
+      bad = true;
+      has_nan = sub_nan;
+      bad_step = done_steps;
+    }
+  }
+
+  // ---- store the cells this tile owns ---------------------------------------------------------------
+  if (vec && local0 >= first_valid) {
+    double2* dv = reinterpret_cast<double2*>(d + cell0);
+#pragma unroll
+    for (int j = 0; j < kM / 2; ++j) dv[j] = make_double2(y[2 * j], y[2 * j + 1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kM; ++j) {
+      const long long cell = cell0 + j;
+      if (local0 + j >= first_valid && cell < (long long)nz) d[cell] = y[j];
     }
   }
   if (__any_sync(0xffffffffu, bad)) {
-    const bool any_nan = __any_sync(0xffffffffu, has_nan);
-    if (lane == 0) {
-      const unsigned long long prev = code[col];  // nonzero from an EARLIER step: that step stays the answer
-      if (prev == 0ull || (prev >> 1) == (unsigned long long)(step + 1))
-        atomicMax(&code[col], ((unsigned long long)(step + 1) << 1) | (any_nan ? 1ull : 0ull));
+    // key = (step << 1) | (NaN ? 0 : 1): the minimum over lanes, tiles and launches is the first bad
+    // step, NaN winning over Inf within it (validate_state order).  ~0 = clean.
+    unsigned long long key = bad ? ((((unsigned long long)bad_step) << 1) | (has_nan ? 0ull : 1ull)) : ~0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+      key = other < key ? other : key;
     }
+    if (lane == 0) atomicMin(&code[col], key);
   }
 }
 
@@ -160,9 +182,9 @@ __global__ void k_stream_finalize(const BatchDev b, const unsigned long long* __
   const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= b.n_cols) return;
   if (b.status) {
-    const unsigned long long c = code[col];
+    const unsigned long long c = code[col];  // ~0 clean, else (step << 1) | (NaN ? 0 : 1)
     const long long s = (long long)(c >> 1);
-    b.status[col] = (c == 0ull) ? 0ll : ((c & 1ull) ? s : -s);
+    b.status[col] = (c == ~0ull) ? 0ll : ((c & 1ull) ? -s : s);
   }
   if (b.summary && full_outlet) {
     const double* o = full_outlet + (size_t)col * (b.steps + 1);
@@ -192,18 +214,35 @@ __global__ void k_stream_init(const BatchDev b, double* __restrict__ ping, unsig
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) ping[i] = b.y0 ? b.y0[i] : 0.0;
   if (blockIdx.x == 0)
-    for (uint32_t c = threadIdx.x; c < b.n_cols; c += blockDim.x) code[c] = 0ull;
+    for (uint32_t c = threadIdx.x; c < b.n_cols; c += blockDim.x) code[c] = ~0ull;
 }
 
 typedef void (*skern_t)(const BatchDev, const double*, double*, uint32_t, unsigned long long*, int, int);
 
-skern_t pick_stream(int method, int arith) {
+template <int FUSE>
+skern_t pick_stream_f(int method, int arith) {
   if (method == CHROM_RK4) {
-    if (arith == CHROM_ARITH_EXACT) return k_single_stream_step<CHROM_RK4, 1>;
-    return arith == CHROM_KARITH_POLY ? k_single_stream_step<CHROM_RK4, 2> : k_single_stream_step<CHROM_RK4, 0>;
+    if (arith == CHROM_ARITH_EXACT) return k_single_stream_step<CHROM_RK4, 1, FUSE>;
+    return arith == CHROM_KARITH_POLY ? k_single_stream_step<CHROM_RK4, 2, FUSE> : k_single_stream_step<CHROM_RK4, 0, FUSE>;
   }
-  if (arith == CHROM_ARITH_EXACT) return k_single_stream_step<CHROM_EULER, 1>;
-  return arith == CHROM_KARITH_POLY ? k_single_stream_step<CHROM_EULER, 2> : k_single_stream_step<CHROM_EULER, 0>;
+  if (arith == CHROM_ARITH_EXACT) return k_single_stream_step<CHROM_EULER, 1, 1>;
+  return arith == CHROM_KARITH_POLY ? k_single_stream_step<CHROM_EULER, 2, 1> : k_single_stream_step<CHROM_EULER, 0, 1>;
+}
+
+skern_t pick_stream(int method, int arith, int fuse) {
+  if (method != CHROM_RK4 || fuse == 1) return pick_stream_f<1>(method, arith);
+  return fuse == 2 ? pick_stream_f<2>(method, arith) : pick_stream_f<4>(method, arith);
+}
+
+// Steps fused per launch: snapshots are taken from the state between launches, so the snapshot
+// stride must be a multiple of the fusion depth.  CHROM_STREAM_FUSE overrides (experiments).
+int stream_fuse(const BatchDev& b) {
+  if (b.method != CHROM_RK4) return 1;
+  int f = 4;
+  if (const char* e = getenv("CHROM_STREAM_FUSE")) f = atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1);
+  while (f > 1 && b.snapshots && b.snapshot_stride && (b.snapshot_stride % f) != 0) f /= 2;
+  while (f > 1 && (uint32_t)f > b.steps) f /= 2;
+  return f;
 }
 
 }  // namespace
@@ -211,23 +250,26 @@ skern_t pick_stream(int method, int arith) {
 bool single_stream_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why) {
   (void)sm_count;
   (void)why;
-  const int H = b.method == CHROM_RK4 ? 4 : 0;
+  const int fuse = stream_fuse(b);
+  const int H = b.method == CHROM_RK4 ? 4 * fuse : 0;
   const int V = kTile - H;
   const long long rest = (long long)b.nz - kTile;
   const int tiles = 1 + (rest > 0 ? (int)((rest + V - 1) / V) : 0);
   g->kind = 3;
   g->M = kM;
   g->L = 32;
-  g->cpw = 0;
+  g->cpw = fuse;
   g->warps_per_col = tiles;
   g->block = dim3(kWarps * 32);
   g->grid = dim3((tiles + kWarps - 1) / kWarps, b.n_cols);
   g->smem = 0;
-  g->launches_per_execute = (uint64_t)b.steps + 2;
-  char buf[200];
-  snprintf(buf, sizeof buf, "single_stream<M=%d,%s,%s> tiles/col=%d halo=%d grid=(%u,%u) block=%d, 1 launch per step", kM,
-           b.method == CHROM_RK4 ? "RK4" : "Euler", (b.arith == CHROM_ARITH_EXACT ? "exact" : (b.arith == CHROM_KARITH_POLY ? "fast-poly" : "fast")), tiles, H, g->grid.x,
-           g->grid.y, kWarps * 32);
+  g->launches_per_execute = ((uint64_t)b.steps + fuse - 1) / fuse + 2;
+  char buf[240];
+  snprintf(buf, sizeof buf,
+           "single_stream<M=%d,%s,%s> tiles/col=%d halo=%d grid=(%u,%u) block=%d, %d fused step(s) per launch, CUDA graph",
+           kM, b.method == CHROM_RK4 ? "RK4" : "Euler",
+           (b.arith == CHROM_ARITH_EXACT ? "exact" : (b.arith == CHROM_KARITH_POLY ? "fast-poly" : "fast")), tiles, H,
+           g->grid.x, g->grid.y, kWarps * 32, fuse);
   g->name = buf;
   return true;
 }
@@ -236,7 +278,8 @@ bool single_stream_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::s
 // allocates n_cols*(nz+1) doubles).  Summaries need the full-rate outlet: b.outlet with stride 1.
 
 cudaError_t single_stream_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s) {
-  skern_t k = pick_stream(b.method, b.arith);
+  const int fuse = g.cpw > 0 ? g.cpw : 1;
+  skern_t k = pick_stream(b.method, b.arith, fuse);
   unsigned long long* code = reinterpret_cast<unsigned long long*>(b.pong + (size_t)b.n_cols * b.nz);
   const size_t plane = (size_t)b.n_cols * b.nz;
   k_stream_init<<<296, 256, 0, s>>>(b, b.ping, code);
@@ -261,12 +304,12 @@ cudaError_t single_stream_launch(const BatchDev& b, const LaunchGeom& g, cudaStr
     cudaError_t e = snapshot(src, 0);
     if (e != cudaSuccess) return e;
   }
-  for (uint32_t step = 0; step < b.steps; ++step) {
-    int out_slot = -1;
-    if (b.outlet && b.outlet_stride && ((step + 1) % b.outlet_stride == 0)) out_slot = (int)((step + 1) / b.outlet_stride);
-    k<<<g.grid, g.block, 0, s>>>(b, src, dst, step, code, out_slot, g.warps_per_col);
-    if (b.snapshots && b.snapshot_stride && ((step + 1) % b.snapshot_stride == 0)) {
-      cudaError_t e = snapshot(dst, (step + 1) / b.snapshot_stride);
+  for (uint32_t step = 0; step < b.steps; step += (uint32_t)fuse) {
+    const int nsub = (int)std::min<uint32_t>((uint32_t)fuse, b.steps - step);
+    k<<<g.grid, g.block, 0, s>>>(b, src, dst, step, code, nsub, g.warps_per_col);
+    const uint32_t done = step + (uint32_t)nsub;
+    if (b.snapshots && b.snapshot_stride && (done % b.snapshot_stride == 0)) {
+      cudaError_t e = snapshot(dst, done / b.snapshot_stride);
       if (e != cudaSuccess) return e;
     }
     double* t = src;

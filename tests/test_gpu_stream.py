@@ -76,6 +76,24 @@ def test_stream_batch_and_strides(ctx):
     assert_bit_equal(r.snapshots[:, 0], y0, "snapshot 0 = initial state")
 
 
+@pytest.mark.parametrize("steps,snap", [(23, 0), (22, 6), (9, 0), (3, 0), (26, 13)])
+def test_stream_fused_steps_tail_and_snapshot_strides(ctx, steps, snap):
+    """Temporal blocking (up to 4 RK4 steps per launch): a step count that is not a multiple of the fusion
+    depth, fewer steps than the depth, and snapshot strides that force depth 2 or 1 — all bit-identical."""
+    nz = 8200 + 37
+    m, dt = long_column(nz)
+    T = dt * steps
+    m.set_injection(cb.TemporalInjection.gaussian(0.3 * T, 0.1 * T, 0.1))
+    y0 = np.random.default_rng(steps).uniform(0.0, 0.02, size=(1, nz))
+    ref = O.solve_single(to_oracle(m), O.RK4, T, steps, y0=y0[0], want_trajectory=True)
+    r, desc = run_gpu(ctx, [m], cb.RK4, T, steps, cb.ARITH_EXACT, y0=y0, snapshot_stride=snap)
+    assert "single_stream" in desc
+    assert_bit_equal(r.outlet[0], ref.outlet, "outlet (every step, sampled inside fused launches)")
+    assert_bit_equal(r.final_state[0], ref.final_state, "final")
+    if snap:
+        assert_bit_equal(r.snapshots[0], ref.trajectory[::snap], "snapshots")
+
+
 def test_stream_status_matches_oracle(ctx):
     """Unstable step on a long column: first non-finite step / class equal to the oracle's."""
     nz, steps = 9000, 300
