@@ -38,6 +38,10 @@ struct alignas(16) SpeciesConst {  // per species, shared memory; {K, feNK} and 
   double feNK2;  // = feNK (second copy so that the forward sweep needs one 128-bit load)
   double lambda;
   double nbar;   // stationary_fraction * (double)port_number
+  double a0rK;   // FAST dense: (1 + fe*lambda) / K      } one 128-bit load
+  double feN;    // FAST dense: fe * nbar (= feNK / K)   }
+  double cgrK;   // FAST dense: (-ue/dz) / K
+  double pad_;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -316,6 +320,69 @@ __device__ __forceinline__ void fast_row(const SpeciesConst* sc, double fe, doub
 #pragma unroll
     for (int s = 0; s < N; ++s) k[s] = (c[s] - up[s]) * cg;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FAST dense, speculative form (the hot path for n <= 8).  Two changes against fast_row, same LU:
+//  * column scaling x_j = y_j / K_j:  (diag(alpha) - p q^T) x = r  <=>  (diag(alpha_i/K_i) - p 1^T) y = r,
+//    so the off-diagonal entries of row i are all -p_i (no n^2 products to build the matrix) and the
+//    scaling by cg = -ue/dz moves into the final product x_j = y_j * (cg / K_j).  Column scaling
+//    commutes with Gaussian elimination: the multipliers and the pivot ROWS are those of the unscaled
+//    matrix.
+//  * the elimination runs without row exchanges and without votes or branches (straight-line code the
+//    scheduler can overlap: reciprocal chain of step i+1 under the rank-1 update of step i) while the
+//    partial-pivoting test of every step is evaluated on the integer pipe; a cell where a row below the
+//    diagonal could hold a larger entry (or a pivot is exactly zero) returns true and is redone by the
+//    caller with the row-exchanging fast_row.  The matrices are close to diagonally dominant
+//    (|a_ri|/|a_ii| <= (nbar_r/nbar_i) K_r c_r / (1 + sum K c)), so this is rare.
+// ------------------------------------------------------------------------------------------------
+template <int N, int I>
+__device__ __forceinline__ void lu_step_spec(double (&a)[N][N], double (&b)[N], bool& redo) {
+  if constexpr (I + 1 < N) {
+    unsigned below = 0u;
+#pragma unroll
+    for (int r = I + 1; r < N; ++r) below = max(below, abs_hi(a[r][I]));
+    redo |= below >= abs_hi(a[I][I]);  // '>=' on the high words: never misses a needed exchange
+  }
+  redo |= (a[I][I] == 0.0);
+  const double rp = fast_rcp(a[I][I]);
+  a[I][I] = rp;
+#pragma unroll
+  for (int r = I + 1; r < N; ++r) {
+    const double l = a[r][I] * rp;
+#pragma unroll
+    for (int q = I + 1; q < N; ++q) a[r][q] = fma(-l, a[I][q], a[r][q]);
+    b[r] = fma(-l, b[I], b[r]);
+  }
+  if constexpr (I + 1 < N) lu_step_spec<N, I + 1>(a, b, redo);
+}
+
+template <int N>
+__device__ __forceinline__ bool fast_row_spec(const SpeciesConst* sc, const double* c, const double* up, double* k) {
+  double S0 = 0.0, S1 = 0.0;  // two chains: the sum is not on the critical path for long
+#pragma unroll
+  for (int s = 0; s < N; s += 2) {
+    S0 = fma(sc[s].K, c[s], S0);
+    if (s + 1 < N) S1 = fma(sc[s + 1].K, c[s + 1], S1);
+  }
+  const double D = 1.0 + (S0 + S1);
+  const double rD2 = fast_rcp(D * D);
+  const double DrD2 = D * rD2;
+  double a[N][N], b[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double np = -(sc[i].feNK * (c[i] * rD2));  // -p_i = -fe nbar_i K_i c_i / D^2
+#pragma unroll
+    for (int j = 0; j < N; ++j) a[i][j] = np;
+    a[i][i] = fma(sc[i].feN, DrD2, sc[i].a0rK) + np;  // alpha_i / K_i - p_i
+    b[i] = c[i] - up[i];
+  }
+  bool redo = false;
+  lu_step_spec<N, 0>(a, b, redo);
+  back_step<N, N - 1>(a, b, k);
+#pragma unroll
+  for (int s = 0; s < N; ++s) k[s] *= sc[s].cgrK;
+  return redo;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -701,6 +768,10 @@ __global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_reside
       q.a0 = 1.0 + fe * sp.lambda;
       q.feNK = fe * (q.nbar * sp.langmuir_k);
       q.feNK2 = q.feNK;
+      q.a0rK = q.a0 / sp.langmuir_k;
+      q.feN = fe * q.nbar;
+      q.cgrK = cg / sp.langmuir_k;
+      q.pad_ = 0.0;
       sc[s] = q;
       tabs[s] = b.tables + (size_t)sp.inj_table * b.steps * ST;
     }
@@ -753,7 +824,13 @@ __global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_reside
           } else if constexpr (ARITH == CHROM_KARITH_STRUCT) {
             if (structured_row<0>(n, sc, cg, c, up, k)) dense_row_scratch(n, sc, cg, c, up, k, my_scratch, sstride);
           } else {
-            fast_row<(N > 0 ? N : 1)>(sc, fe, cg, c, up, k);
+            // speculative exchange-free LU; a warp with a flagged cell redoes it with the row-exchanging LU
+            constexpr int NN = N > 0 ? N : 1;
+            const bool redo = fast_row_spec<NN>(sc, c, up, k);
+            if (__any_sync(0xffffffffu, redo)) {
+              bad |= cold_cell<NN>(sc, fe, cg, SRC, inlet + irow * n, cc, live, st);
+              continue;
+            }
           }
           if (live) bad |= apply_stage<N, EXACT>(st, cc, k, n);
         }
