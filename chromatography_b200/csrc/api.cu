@@ -270,7 +270,7 @@ int32_t build_shard(chrom_cuda_plan* plan, Shard& sh, const chrom_single_col* sc
         return fail(ctx, CHROM_ERR_UNSUPPORTED,
                     "summary on the streaming path (nz > 8192) needs the outlet requested with outlet_stride == 1");
       CUDA_TRY(ctx, sh.ping.alloc(sh.n_cols * state_len, d.stream));
-      CUDA_TRY(ctx, sh.pong.alloc(sh.n_cols * (state_len + 1), d.stream));  // + one status code per column
+      CUDA_TRY(ctx, sh.pong.alloc(sh.n_cols * (state_len + single_stream_extra_doubles()), d.stream));  // + status code + coefficients per column
       b.ping = sh.ping.p;
       b.pong = sh.pong.p;
     }

@@ -65,6 +65,7 @@ cudaError_t single_resident_launch(const BatchDev& b, const LaunchGeom& g, cudaS
 // single_stream.cu — nz beyond the resident capacity: state streamed through HBM/L2, one launch per step
 bool single_stream_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why);
 cudaError_t single_stream_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s);
+size_t single_stream_extra_doubles();  // per column, behind the pong state buffer: status code + coefficients
 
 // multi_resident.cu — LangmuirMulti, per-cell n x n solve
 bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why);

@@ -1,17 +1,20 @@
 // single_stream.cu — LangmuirSingle columns too long for the register-resident path (nz > 8192,
 // e.g. the nz = 2^22 spatial-convergence column of BASELINE config 4): the state streams through
-// HBM/L2 once per time step, all four RK4 stages fused in one pass.
+// HBM/L2, FUSE time steps per pass (temporal blocking), all four RK4 stages of each step fused.
 //
-// Replaces per launch ONE iteration of the time loop (rk4.rs:266-332 / euler.rs:227-269) with
+// Replaces per launch FUSE iterations of the time loop (rk4.rs:266-332 / euler.rs:227-269) with
 // LangmuirSingle::compute_physics (langmuir_single.rs:445-516) evaluated 4 (or 1) times in registers.
 //
 // Tiling: a warp owns 32*M consecutive cells, M per lane (same register scheme as
 // single_resident.cu: one shuffle per lane per stage).  RK4 needs the stage values of the four cells
-// upstream of a tile; instead of exchanging them the tile simply starts 4 cells early and discards
-// its first 4 results (they are recomputed, correctly, by the previous tile): 1.6 % redundant work
-// at M = 8, no inter-CTA communication.  Tile 0 starts at the inlet and keeps everything.
+// upstream of a tile per time step; instead of exchanging them the tile starts 4*FUSE cells early and
+// discards its first 4*FUSE results (they are recomputed, correctly, by the previous tile): no
+// inter-CTA communication.  Default M = 16, FUSE = 8: halo 32 of 512 cells (6.3 % redundant work),
+// the state crosses L2/HBM once per 8 steps.  Tile 0 starts at the inlet and keeps everything.
 // Algorithmic HBM traffic: 16 B per cell-step (read y_n, write y_n+1); both ping-pong buffers of
-// the 2^22 column (67 MB) fit the 126 MB L2.
+// the 2^22 column (67 MB) fit the 126 MB L2.  Per-column coefficients are derived once per solve
+// (k_stream_coef); which sub-steps sample the outlet is decided on the host (no 64-bit division
+// in the kernel).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -23,9 +26,8 @@
 namespace chrom {
 namespace {
 
-constexpr int kM = 8;           // cells per lane
-constexpr int kTile = 32 * kM;  // cells per warp tile
-constexpr int kWarps = 4;       // warps per CTA
+constexpr int kCoefSlots = 8;  // doubles reserved per column for Coef<ARITH> (sizeof <= 64)
+constexpr int kMaxWarps = 4;  // warps per CTA (upper bound; the launch picks 1..4)
 
 // status word while streaming: ~0 = clean, else (step << 1) | (NaN ? 0 : 1), merged with atomicMin: the first
 // bad step wins, NaN over Inf within it (solver/mod.rs:519-548).
@@ -33,16 +35,20 @@ constexpr int kWarps = 4;       // warps per CTA
 // FUSE consecutive time steps are advanced per launch (temporal blocking): the state crosses HBM/L2
 // once per FUSE steps, the halo grows to 4*FUSE cells (FUSE = 4: 6.5 % redundant work at M = 8).
 // Outlet samples and the non-finite scan are taken after every sub-step, on cells no halo touches.
-template <int METHOD, int ARITH, int FUSE>
-__global__ void __launch_bounds__(kWarps * 32)
+// kM cells per lane (a warp tile is 32*kM cells): larger kM = more independent cells per lane for the
+// FP64 pipe and a smaller halo fraction, at 6 registers per cell.
+template <int METHOD, int ARITH, int FUSE, int kM>
+__global__ void __launch_bounds__(kMaxWarps * 32)
     k_single_stream_step(const BatchDev b, const double* __restrict__ src, double* __restrict__ dst, uint32_t step,
-                         unsigned long long* __restrict__ code, int nsub, int tiles_per_col) {
+                         unsigned long long* __restrict__ code, int nsub, int tiles_per_col, uint32_t out_mask,
+                         uint32_t out_slot0) {
   constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
+  constexpr int kTile = 32 * kM;
   constexpr int H = (METHOD == CHROM_RK4) ? 4 * FUSE : 0;  // RK4 stage values reach 4 cells upstream per step
   constexpr int V = kTile - H;                             // cells a non-first tile contributes
   using Q = Coef<ARITH>;
   const int lane = threadIdx.x & 31;
-  const int tile = (int)(blockIdx.x * kWarps + (threadIdx.x >> 5));
+  const int tile = (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
   const uint32_t col = blockIdx.y;
   if (tile >= tiles_per_col) return;
   const uint32_t nz = b.nz;
@@ -55,10 +61,10 @@ __global__ void __launch_bounds__(kWarps * 32)
   const int first_valid = (tile == 0) ? 0 : H;  // tile-local index of the first cell this tile owns
   const int local0 = lane * kM;                 // tile-local index of this lane's first cell
 
-  const chrom_single_col cp = b.scols[col];
-  Q q;
-  q.init(cp);
-  const double* __restrict__ tab = b.tables + ((size_t)cp.inj_table * b.steps + step) * ST;
+  // per-column coefficients, derived once per solve by k_stream_coef (their IEEE divisions would cost ~9 %
+  // of a launch if every thread repeated them): kCoefSlots doubles per column behind the status codes
+  const Q q = *reinterpret_cast<const Q*>(reinterpret_cast<const double*>(code + b.n_cols) + (size_t)col * kCoefSlots);
+  const double* __restrict__ tab = b.tables + ((size_t)b.scols[col].inj_table * b.steps + step) * ST;
   const double dt = b.dt, h2 = b.half_dt, h6 = b.sixth_dt;
 
   const double* __restrict__ s = src + (size_t)col * nz;
@@ -85,6 +91,13 @@ __global__ void __launch_bounds__(kWarps * 32)
     const double up = __shfl_up_sync(0xffffffffu, last, 1);
     return inlet_lane ? inlet : up;  // lane 0 of a later tile gets its own value back: halo, discarded
   };
+
+  // cells [j_lo, j_hi) of this lane are owned by the tile and inside the column
+  const int j_lo = min(kM, max(0, first_valid - local0));
+  const int j_hi = (int)min((long long)kM, max(0ll, (long long)nz - cell0));
+  const bool full_lane = (j_lo == 0) && (j_hi == kM);
+  const long long oj = (long long)nz - 1 - cell0;
+  const int out_j = (b.outlet != nullptr && oj >= (long long)j_lo && oj < (long long)j_hi) ? (int)oj : -1;
 
   bool bad = false, has_nan = false;
   uint32_t bad_step = 0;
@@ -131,20 +144,31 @@ __global__ void __launch_bounds__(kWarps * 32)
       }
     }
     // ---- per sub-step: outlet sample and non-finite scan on the cells this tile owns ------------------
+    // (which sub-steps sample the outlet, and into which slot, is decided on the host: out_mask/out_slot0)
     const uint32_t done_steps = step + (uint32_t)f + 1u;
-    const bool want_out = b.outlet && b.outlet_stride && (done_steps % b.outlet_stride == 0u);
-    bool sub_bad = false, sub_nan = false;
+    bool sub_bad;
+    if (full_lane) {  // every cell of this lane is owned and inside the column: one max over the high words
+      unsigned m = 0u;
 #pragma unroll
-    for (int j = 0; j < kM; ++j) {
-      const long long cell = cell0 + j;
-      if (local0 + j >= first_valid && cell < (long long)nz) {
-        sub_bad |= hi_nonfinite(abs_hi(y[j]));
-        sub_nan |= (y[j] != y[j]);
-        if (want_out && cell == (long long)nz - 1)
-          b.outlet[(size_t)col * b.n_out + done_steps / b.outlet_stride] = y[j];
-      }
+      for (int j = 0; j < kM; ++j) m = max(m, abs_hi(y[j]));
+      sub_bad = hi_nonfinite(m);
+    } else {  // halo lanes of a tile and the ragged end of the column
+      sub_bad = false;
+#pragma unroll
+      for (int j = 0; j < kM; ++j)
+        if (j >= j_lo && j < j_hi) sub_bad |= hi_nonfinite(abs_hi(y[j]));
     }
-    if (sub_bad && !bad) {  // remember the FIRST bad sub-step of this lane
+    if (out_j >= 0 && ((out_mask >> f) & 1u)) {  // the one lane that holds cell nz-1
+      double v = y[0];
+#pragma unroll
+      for (int j = 1; j < kM; ++j) v = (out_j == j) ? y[j] : v;
+      b.outlet[(size_t)col * b.n_out + out_slot0 + (uint32_t)__popc(out_mask & ((1u << f) - 1u))] = v;
+    }
+    if (sub_bad && !bad) {  // remember the FIRST bad sub-step of this lane (rare: the NaN scan lives here)
+      bool sub_nan = false;
+#pragma unroll
+      for (int j = 0; j < kM; ++j)
+        if (j >= j_lo && j < j_hi) sub_nan |= (y[j] != y[j]);
       bad = true;
       has_nan = sub_nan;
       bad_step = done_steps;
@@ -217,40 +241,72 @@ __global__ void k_stream_init(const BatchDev b, double* __restrict__ ping, unsig
     for (uint32_t c = threadIdx.x; c < b.n_cols; c += blockDim.x) code[c] = ~0ull;
 }
 
-typedef void (*skern_t)(const BatchDev, const double*, double*, uint32_t, unsigned long long*, int, int);
-
-template <int FUSE>
-skern_t pick_stream_f(int method, int arith) {
-  if (method == CHROM_RK4) {
-    if (arith == CHROM_ARITH_EXACT) return k_single_stream_step<CHROM_RK4, 1, FUSE>;
-    return arith == CHROM_KARITH_POLY ? k_single_stream_step<CHROM_RK4, 2, FUSE> : k_single_stream_step<CHROM_RK4, 0, FUSE>;
-  }
-  if (arith == CHROM_ARITH_EXACT) return k_single_stream_step<CHROM_EULER, 1, 1>;
-  return arith == CHROM_KARITH_POLY ? k_single_stream_step<CHROM_EULER, 2, 1> : k_single_stream_step<CHROM_EULER, 0, 1>;
+template <int ARITH>
+__global__ void k_stream_coef(const BatchDev b, unsigned long long* __restrict__ code) {
+  static_assert(sizeof(Coef<ARITH>) <= kCoefSlots * sizeof(double), "Coef does not fit its slot");
+  const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= b.n_cols) return;
+  Coef<ARITH> q;
+  q.init(b.scols[col]);
+  *reinterpret_cast<Coef<ARITH>*>(reinterpret_cast<double*>(code + b.n_cols) + (size_t)col * kCoefSlots) = q;
 }
 
-skern_t pick_stream(int method, int arith, int fuse) {
-  if (method != CHROM_RK4 || fuse == 1) return pick_stream_f<1>(method, arith);
-  return fuse == 2 ? pick_stream_f<2>(method, arith) : pick_stream_f<4>(method, arith);
+typedef void (*skern_t)(const BatchDev, const double*, double*, uint32_t, unsigned long long*, int, int, uint32_t,
+                        uint32_t);
+
+template <int FUSE, int M>
+skern_t pick_stream_f(int method, int arith) {
+  if (method == CHROM_RK4) {
+    if (arith == CHROM_ARITH_EXACT) return k_single_stream_step<CHROM_RK4, 1, FUSE, M>;
+    return arith == CHROM_KARITH_POLY ? k_single_stream_step<CHROM_RK4, 2, FUSE, M> : k_single_stream_step<CHROM_RK4, 0, FUSE, M>;
+  }
+  if (arith == CHROM_ARITH_EXACT) return k_single_stream_step<CHROM_EULER, 1, 1, M>;
+  return arith == CHROM_KARITH_POLY ? k_single_stream_step<CHROM_EULER, 2, 1, M> : k_single_stream_step<CHROM_EULER, 0, 1, M>;
+}
+
+template <int M>
+skern_t pick_stream_m(int method, int arith, int fuse) {
+  if (method != CHROM_RK4 || fuse == 1) return pick_stream_f<1, M>(method, arith);
+  if (fuse == 2) return pick_stream_f<2, M>(method, arith);
+  return fuse == 4 ? pick_stream_f<4, M>(method, arith) : pick_stream_f<8, M>(method, arith);
+}
+
+skern_t pick_stream(int method, int arith, int fuse, int m) {
+  return m == 16 ? pick_stream_m<16>(method, arith, fuse) : pick_stream_m<8>(method, arith, fuse);
 }
 
 // Steps fused per launch: snapshots are taken from the state between launches, so the snapshot
 // stride must be a multiple of the fusion depth.  CHROM_STREAM_FUSE overrides (experiments).
 int stream_fuse(const BatchDev& b) {
   if (b.method != CHROM_RK4) return 1;
-  int f = 4;
-  if (const char* e = getenv("CHROM_STREAM_FUSE")) f = atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1);
+  int f = 8;
+  if (const char* e = getenv("CHROM_STREAM_FUSE")) f = atoi(e) >= 8 ? 8 : (atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1));
   while (f > 1 && b.snapshots && b.snapshot_stride && (b.snapshot_stride % f) != 0) f /= 2;
   while (f > 1 && (uint32_t)f > b.steps) f /= 2;
   return f;
 }
 
+// Cells per lane and warps per CTA.  CHROM_STREAM_M / CHROM_STREAM_WARPS override (experiments).
+int stream_m() {
+  int m = 16;
+  if (const char* e = getenv("CHROM_STREAM_M")) m = atoi(e) >= 16 ? 16 : 8;
+  return m;
+}
+int stream_warps() {
+  int w = kMaxWarps;
+  if (const char* e = getenv("CHROM_STREAM_WARPS")) w = std::max(1, std::min(kMaxWarps, atoi(e)));
+  return w;
+}
+
 }  // namespace
+
+size_t single_stream_extra_doubles() { return 1 + kCoefSlots; }
 
 bool single_stream_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why) {
   (void)sm_count;
   (void)why;
   const int fuse = stream_fuse(b);
+  const int kM = stream_m(), kWarps = stream_warps(), kTile = 32 * kM;
   const int H = b.method == CHROM_RK4 ? 4 * fuse : 0;
   const int V = kTile - H;
   const long long rest = (long long)b.nz - kTile;
@@ -263,7 +319,7 @@ bool single_stream_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::s
   g->block = dim3(kWarps * 32);
   g->grid = dim3((tiles + kWarps - 1) / kWarps, b.n_cols);
   g->smem = 0;
-  g->launches_per_execute = ((uint64_t)b.steps + fuse - 1) / fuse + 2;
+  g->launches_per_execute = ((uint64_t)b.steps + fuse - 1) / fuse + 3;
   char buf[240];
   snprintf(buf, sizeof buf,
            "single_stream<M=%d,%s,%s> tiles/col=%d halo=%d grid=(%u,%u) block=%d, %d fused step(s) per launch, CUDA graph",
@@ -274,15 +330,21 @@ bool single_stream_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::s
   return true;
 }
 
-// b.ping: [n_cols][nz]; b.pong: [n_cols][nz] followed by n_cols 64-bit status codes (the caller
-// allocates n_cols*(nz+1) doubles).  Summaries need the full-rate outlet: b.outlet with stride 1.
+// b.ping: [n_cols][nz]; b.pong: [n_cols][nz] followed by n_cols 64-bit status codes and n_cols
+// coefficient slots (the caller allocates n_cols*(nz + 1 + single_stream_extra_doubles()) doubles).  Summaries need the full-rate outlet: b.outlet with stride 1.
 
 cudaError_t single_stream_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s) {
   const int fuse = g.cpw > 0 ? g.cpw : 1;
-  skern_t k = pick_stream(b.method, b.arith, fuse);
+  skern_t k = pick_stream(b.method, b.arith, fuse, g.M);
   unsigned long long* code = reinterpret_cast<unsigned long long*>(b.pong + (size_t)b.n_cols * b.nz);
   const size_t plane = (size_t)b.n_cols * b.nz;
   k_stream_init<<<296, 256, 0, s>>>(b, b.ping, code);
+  {
+    const dim3 cg((b.n_cols + 127) / 128), cb(128);
+    if (b.arith == CHROM_ARITH_EXACT) k_stream_coef<1><<<cg, cb, 0, s>>>(b, code);
+    else if (b.arith == CHROM_KARITH_POLY) k_stream_coef<2><<<cg, cb, 0, s>>>(b, code);
+    else k_stream_coef<0><<<cg, cb, 0, s>>>(b, code);
+  }
   double* src = b.ping;
   double* dst = b.pong;
   if (b.outlet) {  // slot 0: the outlet of the initial state
@@ -306,7 +368,16 @@ cudaError_t single_stream_launch(const BatchDev& b, const LaunchGeom& g, cudaStr
   }
   for (uint32_t step = 0; step < b.steps; step += (uint32_t)fuse) {
     const int nsub = (int)std::min<uint32_t>((uint32_t)fuse, b.steps - step);
-    k<<<g.grid, g.block, 0, s>>>(b, src, dst, step, code, nsub, g.warps_per_col);
+    uint32_t out_mask = 0u, out_slot0 = 0u;  // sub-steps of this launch that sample the outlet, first slot
+    if (b.outlet && b.outlet_stride)
+      for (int f = 0; f < nsub; ++f) {
+        const uint64_t ds = (uint64_t)step + (uint64_t)f + 1u;
+        if (ds % b.outlet_stride == 0) {
+          if (!out_mask) out_slot0 = (uint32_t)(ds / b.outlet_stride);
+          out_mask |= 1u << f;
+        }
+      }
+    k<<<g.grid, g.block, 0, s>>>(b, src, dst, step, code, nsub, g.warps_per_col, out_mask, out_slot0);
     const uint32_t done = step + (uint32_t)nsub;
     if (b.snapshots && b.snapshot_stride && (done % b.snapshot_stride == 0)) {
       cudaError_t e = snapshot(dst, done / b.snapshot_stride);
