@@ -69,6 +69,29 @@ def units_of(spec: dict, n_cols: int) -> float:
     return float(n_cols) * spec["nz"] * spec["steps"] * 4.0
 
 
+def measured_peaks() -> dict:
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
+def ncu_traffic(family: str, workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+    `ncu --set full` capture of this workload (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py).
+    Not measured in this run: a number taken under a profiler is never a bench value, this is a counter."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)
+        e = t[workload]
+        if e.get("kernel_family") != family:
+            return None, f"profiles/ncu_traffic.json has {e.get('kernel_family')} for {workload}, this run used {family}"
+        return e["dram_bytes_per_launch"], e["source"]
+    except (OSError, ValueError, KeyError):
+        return None, "no ncu capture committed for this workload"
+
+
 # ---- host cores actually usable --------------------------------------------------------------------
 def host_cores() -> int:
     try:
@@ -350,6 +373,7 @@ def main():
     clocks = sampler.stop() if sampler else None
     t_dev_ms = max_over_ranks(sum(kernel_ms))
     value = aggregate_value(ranks, units_rank * args.steps, sum(kernel_ms))
+    launches_value = launches
     st = plan.download().status
     n_bad = int(np.count_nonzero(st))
     plan.close()
@@ -392,6 +416,32 @@ def main():
         e2e = {"value": sum_over_ranks(units_rank) * e_steps / (e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e_ms / e_steps,
                "steps": e_steps, "api": "chrom_cuda_solve_%s_batch, pinned host buffers" % spec["kind"]}
+        # The same call in the sweep mode the ABI offers: per-column on-device summaries
+        # (area, first moment, max, time of max) + final state + status instead of the full-rate outlet
+        # series.  Reported beside e2e, never instead of it: the D2H volume is what differs.
+        if spec["kind"] == "single" and spec["nz"] <= 8192:
+            summ, p4 = pinned_array(lib, (n_cols, 4))
+
+            def call_summary():
+                rc = lib.chrom_cuda_solve_single_batch(ctx._h, C.byref(cfg), inp["cols"], n_cols, dp(tables),
+                                                       tables.shape[0], None, None, None, dp(final), dp(summ),
+                                                       status.ctypes.data_as(C.POINTER(C.c_int64)))
+                ctx.check(rc)
+                return ctx.timing()
+
+            call_summary()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                tm = call_summary()
+                launches += int(tm["kernel_launches"])
+            barrier()
+            s_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            e2e["summary_mode"] = {"value": sum_over_ranks(units_rank) * e_steps / (s_ms * 1e-3), "unit": UNIT,
+                                   "h2d_bytes_per_step": int(tm["h2d_bytes"]), "d2h_bytes_per_step": int(tm["d2h_bytes"]),
+                                   "ms_per_step": s_ms / e_steps,
+                                   "returns": "summary[n_cols][4] + final_state + status (no outlet series)"}
+            lib.chrom_cuda_host_free(p4)
         for p in (p1, p2, p3):
             lib.chrom_cuda_host_free(p)
 
@@ -408,19 +458,42 @@ def main():
     if rank == 0:
         per_rank_rate = units_rank * args.steps / (sum(kernel_ms) * 1e-3)
         achieved = per_rank_rate * spec["flops"] / 1e12
+        # dominant kernel: launches of the solver kernel per execute and its average duration (CUDA events)
+        solver_launches = max(1, int(launches_value / args.steps) - (3 if "single_stream" in desc else 0))
+        launch_ms = (sum(kernel_ms) / args.steps) / solver_launches
+        family = desc.split("<")[0]
+        traffic, traffic_src = ncu_traffic(family, args.workload)
+        # algorithmic HBM bytes per solver launch: streaming path 16 B per cell-step;
+        # resident paths only write their sampled outputs (outlet series + final state)
+        if "single_stream" in desc:
+            fuse = int(desc.split(" fused")[0].split()[-1])
+            alg_bytes = 16.0 * spec["nz"] * n_cols * fuse
+        else:
+            alg_bytes = 8.0 * n_cols * spec["n_species"] * (spec["steps"] + 1 + spec["nz"])
+        hbm_peak = measured_peaks().get("hbm_gbs")
+        hbm_gbs = alg_bytes / (launch_ms * 1e-3) / 1e9
+        out_gb = 8.0 * n_cols * spec["n_species"] * (spec["steps"] + 1) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W_,
             "ms_per_step": t_dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": spec["label"], "columns_per_gpu": n_cols, "arith": "fast (1 reciprocal per "
-                       "cell-stage, FMA; <=1e-9 rel. vs reference order)", "kernel": desc,
-                       "l2": "256 MiB buffer written between timed iterations (L2 flush); outputs 5.2 GB/step >> L2",
+            "config": {"workload": spec["label"], "columns_per_gpu": n_cols,
+                       "arith": "fast (FMA contraction, one refined MUFU reciprocal per cell-stage / pivot; <=1e-9 "
+                                "relative to the reference's operation order)",
+                       "kernel": desc,
+                       "l2": f"256 MiB buffer written between timed iterations (L2 flush); outputs {out_gb:.2f} GB/step",
                        "columns_with_nonfinite_status": n_bad},
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tflops if peak_tflops else None, "traffic": None,
+                         "frac": achieved / peak_tflops if peak_tflops else None,
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "DFMA micro-benchmark in this run (chrom_cuda_measure_fp64_peak); "
-                                        "MEASURED_PEAKS.json has no FP64 entry",
-                         "flops_per_cell_stage": spec["flops"]},
+                                        "MEASURED_PEAKS.json holds HBM and bf16 peaks only, no FP64 entry",
+                         "flops_per_cell_stage": spec["flops"],
+                         "kernel_launch_ms": launch_ms, "kernel_launches_per_step": solver_launches,
+                         "algorithmic_bytes": alg_bytes,
+                         "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": hbm_gbs / hbm_peak if hbm_peak else None,
+                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if hbm_peak else "absent"}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "wall_ms_per_step_incl_flush": wall_ms / args.steps,
         }
