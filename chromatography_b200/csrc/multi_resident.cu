@@ -1,959 +1,52 @@
-// multi_resident.cu — shared-memory-resident LangmuirMulti time integrator (RK4 / Euler).
-//
-// Replaces, for a batch of columns and ALL time steps in one launch:
-//   RK4Solver::solve / EulerSolver::solve        src/solver/methods/rk4.rs:266-332, euler.rs:227-269
-//   LangmuirMulti::compute_physics / compute_row src/models/langmuir_multi.rs:717-899 (770-840)
-//   LangmuirMulti::jacobian                      src/models/langmuir_multi.rs:627-668
-//   inverse_propagation + `inv * grad`           src/models/langmuir_multi.rs:674-686, 838 (nalgebra 0.34)
-//   validate_state                               src/solver/mod.rs:514-553
-//
-// Layout: one CTA owns one column.  Its state lives in shared memory as [array][species][nz]
-// (species-major, the reference's nalgebra column-major nz x n matrix): y (state at t_n), acc
-// (running weighted slope) and two stage buffers u0/u1 (ping-pong, so a cell may read its upstream
-// neighbour while that neighbour's thread writes the next stage).  One thread processes one cell
-// at a time — all n species — with the n x n matrix I + Fe*M in REGISTERS:
-//   FAST : LU with partial pivoting applied directly to the gradient (no explicit inverse);
-//          pivot search on the integer pipe, row swaps only when some lane of the warp needs one.
-//   EXACT: nalgebra's try_inverse restated operation by operation (closed forms n<=4, partial-pivot
-//          LU + two triangular solves on the permuted identity n>=5), then gemv in nalgebra's order.
-// Cells are strided over threads (cell = tid + c*T): conflict-free shared-memory access.
-// One __syncthreads per stage; the last one of a step carries the non-finite flag.
+// multi_resident.cu — host side of the shared-memory-resident LangmuirMulti integrator: kernel lookup,
+// launch geometry and launch.  The device code lives in multi_kernels.cuh and is instantiated per species
+// count by multi_inst.cu (one object per n, built in parallel).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
-#include "arith.cuh"
 #include "kernels.h"
 
 namespace chrom {
+
+typedef void (*mkern_t)(const BatchDev, double*);
+mkern_t multi_pick_0(int method, int arith);  // runtime n (9 .. 64)
+mkern_t multi_pick_1(int method, int arith);
+mkern_t multi_pick_2(int method, int arith);
+mkern_t multi_pick_3(int method, int arith);
+mkern_t multi_pick_4(int method, int arith);
+mkern_t multi_pick_5(int method, int arith);
+mkern_t multi_pick_6(int method, int arith);
+mkern_t multi_pick_7(int method, int arith);
+mkern_t multi_pick_8(int method, int arith);
+
 namespace {
 
-constexpr int kNMax = 64;      // largest runtime n
-constexpr int kNMaxDecl = kNMax;
+constexpr int kNMax = 64;  // largest runtime n (multi_kernels.cuh)
 
-struct alignas(16) SpeciesConst {  // per species, shared memory; {K, feNK} and {a0, feNK2} load as 128-bit pairs
-  double K;      // langmuir_k
-  double feNK;   // FAST: fe * nbar * K
-  double a0;     // FAST: 1 + fe*lambda
-  double feNK2;  // = feNK (second copy so that the forward sweep needs one 128-bit load)
-  double lambda;
-  double nbar;   // stationary_fraction * (double)port_number
-  double a0rK;   // FAST dense: (1 + fe*lambda) / K      } one 128-bit load
-  double feN;    // FAST dense: fe * nbar (= feNK / K)   }
-  double cgrK;   // FAST dense: (-ue/dz) / K
-  double pad_;
-};
+// bytes of one SpeciesConst in shared memory (multi_kernels.cuh: 10 doubles, 16-byte aligned)
+constexpr size_t kSpeciesConstBytes = 10 * sizeof(double);
 
-// ------------------------------------------------------------------------------------------------
-// EXACT: nalgebra try_inverse + gemv, column-major a[i + j*N], one IEEE op per reference op.
-// ------------------------------------------------------------------------------------------------
-template <int N>
-__device__ bool exact_try_inverse(const double* m, double* out) {
-  if constexpr (N == 1) {
-    if (m[0] == 0.0) return false;
-    out[0] = x_div(1.0, m[0]);
-    return true;
-  } else if constexpr (N == 2) {
-    const double m11 = m[0], m21 = m[1], m12 = m[2], m22 = m[3];
-    const double det = x_sub(x_mul(m11, m22), x_mul(m21, m12));
-    if (det == 0.0) return false;
-    out[0] = x_div(m22, det);
-    out[2] = x_div(-m12, det);
-    out[1] = x_div(-m21, det);
-    out[3] = x_div(m11, det);
-    return true;
-  } else if constexpr (N == 3) {
-    const double m11 = m[0], m21 = m[1], m31 = m[2], m12 = m[3], m22 = m[4], m32 = m[5], m13 = m[6], m23 = m[7],
-                 m33 = m[8];
-    const double minor_m12_m23 = x_sub(x_mul(m22, m33), x_mul(m32, m23));
-    const double minor_m11_m23 = x_sub(x_mul(m21, m33), x_mul(m31, m23));
-    const double minor_m11_m22 = x_sub(x_mul(m21, m32), x_mul(m31, m22));
-    const double det =
-        x_add(x_sub(x_mul(m11, minor_m12_m23), x_mul(m12, minor_m11_m23)), x_mul(m13, minor_m11_m22));
-    if (det == 0.0) return false;
-    out[0] = x_div(minor_m12_m23, det);
-    out[3] = x_div(x_sub(x_mul(m13, m32), x_mul(m33, m12)), det);
-    out[6] = x_div(x_sub(x_mul(m12, m23), x_mul(m22, m13)), det);
-    out[1] = x_div(-minor_m11_m23, det);
-    out[4] = x_div(x_sub(x_mul(m11, m33), x_mul(m31, m13)), det);
-    out[7] = x_div(x_sub(x_mul(m13, m21), x_mul(m23, m11)), det);
-    out[2] = x_div(minor_m11_m22, det);
-    out[5] = x_div(x_sub(x_mul(m12, m31), x_mul(m32, m11)), det);
-    out[8] = x_div(x_sub(x_mul(m11, m22), x_mul(m21, m12)), det);
-    return true;
-  } else if constexpr (N == 4) {
-    // do_inverse4: six-term cofactors a*b*c -/+ ..., evaluated left to right
-#define T3(s, a, b, c) (s x_mul(x_mul(a, b), c))
-#define COF(t0, t1, t2, t3, t4, t5) x_add(x_add(x_add(x_add(x_add(t0, t1), t2), t3), t4), t5)
-    const double c00 = COF(T3(+, m[5], m[10], m[15]), T3(-, m[5], m[11], m[14]), T3(-, m[9], m[6], m[15]),
-                           T3(+, m[9], m[7], m[14]), T3(+, m[13], m[6], m[11]), T3(-, m[13], m[7], m[10]));
-    const double c01 = COF(T3(+, -m[4], m[10], m[15]), T3(+, m[4], m[11], m[14]), T3(+, m[8], m[6], m[15]),
-                           T3(-, m[8], m[7], m[14]), T3(-, m[12], m[6], m[11]), T3(+, m[12], m[7], m[10]));
-    const double c02 = COF(T3(+, m[4], m[9], m[15]), T3(-, m[4], m[11], m[13]), T3(-, m[8], m[5], m[15]),
-                           T3(+, m[8], m[7], m[13]), T3(+, m[12], m[5], m[11]), T3(-, m[12], m[7], m[9]));
-    const double c03 = COF(T3(+, -m[4], m[9], m[14]), T3(+, m[4], m[10], m[13]), T3(+, m[8], m[5], m[14]),
-                           T3(-, m[8], m[6], m[13]), T3(-, m[12], m[5], m[10]), T3(+, m[12], m[6], m[9]));
-    const double det =
-        x_add(x_add(x_add(x_mul(m[0], c00), x_mul(m[1], c01)), x_mul(m[2], c02)), x_mul(m[3], c03));
-    if (det == 0.0) return false;
-    double inv[16];
-    inv[0] = c00;
-    inv[1] = COF(T3(+, -m[1], m[10], m[15]), T3(+, m[1], m[11], m[14]), T3(+, m[9], m[2], m[15]),
-                 T3(-, m[9], m[3], m[14]), T3(-, m[13], m[2], m[11]), T3(+, m[13], m[3], m[10]));
-    inv[2] = COF(T3(+, m[1], m[6], m[15]), T3(-, m[1], m[7], m[14]), T3(-, m[5], m[2], m[15]),
-                 T3(+, m[5], m[3], m[14]), T3(+, m[13], m[2], m[7]), T3(-, m[13], m[3], m[6]));
-    inv[3] = COF(T3(+, -m[1], m[6], m[11]), T3(+, m[1], m[7], m[10]), T3(+, m[5], m[2], m[11]),
-                 T3(-, m[5], m[3], m[10]), T3(-, m[9], m[2], m[7]), T3(+, m[9], m[3], m[6]));
-    inv[4] = c01;
-    inv[5] = COF(T3(+, m[0], m[10], m[15]), T3(-, m[0], m[11], m[14]), T3(-, m[8], m[2], m[15]),
-                 T3(+, m[8], m[3], m[14]), T3(+, m[12], m[2], m[11]), T3(-, m[12], m[3], m[10]));
-    inv[6] = COF(T3(+, -m[0], m[6], m[15]), T3(+, m[0], m[7], m[14]), T3(+, m[4], m[2], m[15]),
-                 T3(-, m[4], m[3], m[14]), T3(-, m[12], m[2], m[7]), T3(+, m[12], m[3], m[6]));
-    inv[7] = COF(T3(+, m[0], m[6], m[11]), T3(-, m[0], m[7], m[10]), T3(-, m[4], m[2], m[11]),
-                 T3(+, m[4], m[3], m[10]), T3(+, m[8], m[2], m[7]), T3(-, m[8], m[3], m[6]));
-    inv[8] = c02;
-    inv[9] = COF(T3(+, -m[0], m[9], m[15]), T3(+, m[0], m[11], m[13]), T3(+, m[8], m[1], m[15]),
-                 T3(-, m[8], m[3], m[13]), T3(-, m[12], m[1], m[11]), T3(+, m[12], m[3], m[9]));
-    inv[10] = COF(T3(+, m[0], m[5], m[15]), T3(-, m[0], m[7], m[13]), T3(-, m[4], m[1], m[15]),
-                  T3(+, m[4], m[3], m[13]), T3(+, m[12], m[1], m[7]), T3(-, m[12], m[3], m[5]));
-    inv[11] = COF(T3(+, -m[0], m[5], m[11]), T3(+, m[0], m[7], m[9]), T3(+, m[4], m[1], m[11]),
-                  T3(-, m[4], m[3], m[9]), T3(-, m[8], m[1], m[7]), T3(+, m[8], m[3], m[5]));
-    inv[12] = c03;
-    inv[13] = COF(T3(+, m[0], m[9], m[14]), T3(-, m[0], m[10], m[13]), T3(-, m[8], m[1], m[14]),
-                  T3(+, m[8], m[2], m[13]), T3(+, m[12], m[1], m[10]), T3(-, m[12], m[2], m[9]));
-    inv[14] = COF(T3(+, -m[0], m[5], m[14]), T3(+, m[0], m[6], m[13]), T3(+, m[4], m[1], m[14]),
-                  T3(-, m[4], m[2], m[13]), T3(-, m[12], m[1], m[6]), T3(+, m[12], m[2], m[5]));
-    inv[15] = COF(T3(+, m[0], m[5], m[10]), T3(-, m[0], m[6], m[9]), T3(-, m[4], m[1], m[10]),
-                  T3(+, m[4], m[2], m[9]), T3(+, m[8], m[1], m[6]), T3(-, m[8], m[2], m[5]));
-#undef T3
-#undef COF
-    const double inv_det = x_div(1.0, det);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) out[k] = x_mul(inv[k], inv_det);
-    return true;
-  } else {
-  // N >= 5: lu::try_invert_to
-  double a[N * N];
-#pragma unroll
-  for (int k = 0; k < N * N; ++k) {
-    a[k] = m[k];
-    out[k] = ((k % N) == (k / N)) ? 1.0 : 0.0;
-  }
-  for (int i = 0; i < N; ++i) {
-    int piv = i;
-    double the_max = fabs(a[i + i * N]);
-    for (int r = i + 1; r < N; ++r) {
-      const double v = fabs(a[r + i * N]);
-      if (v > the_max) {
-        the_max = v;
-        piv = r;
-      }
-    }
-    const double diag = a[piv + i * N];
-    if (diag == 0.0) return false;
-    if (piv != i) {
-      for (int j = 0; j < N; ++j) {
-        const double t = out[i + j * N];
-        out[i + j * N] = out[piv + j * N];
-        out[piv + j * N] = t;
-      }
-      for (int j = 0; j <= i; ++j) {  // columns ..i of the L part, and the coefficient column i
-        const double t = a[i + j * N];
-        a[i + j * N] = a[piv + j * N];
-        a[piv + j * N] = t;
-      }
-    }
-    const double inv_diag = x_div(1.0, diag);
-    for (int r = i + 1; r < N; ++r) a[r + i * N] = x_mul(a[r + i * N], inv_diag);
-    for (int k = i + 1; k < N; ++k) {
-      if (piv != i) {
-        const double t = a[i + k * N];
-        a[i + k * N] = a[piv + k * N];
-        a[piv + k * N] = t;
-      }
-      const double neg_pivot = -a[i + k * N];
-      for (int r = i + 1; r < N; ++r) a[r + k * N] = x_add(x_mul(neg_pivot, a[r + i * N]), a[r + k * N]);
-    }
-  }
-  for (int c = 0; c < N; ++c)
-    for (int i = 0; i + 1 < N; ++i) {
-      const double coeff = out[i + c * N];  // b[i] / 1.0
-      for (int r = i + 1; r < N; ++r) out[r + c * N] = x_add(x_mul(-coeff, a[r + i * N]), out[r + c * N]);
-    }
-  for (int c = 0; c < N; ++c)
-    for (int i = N - 1; i >= 0; --i) {
-      const double diag = a[i + i * N];
-      if (diag == 0.0) return false;
-      const double coeff = x_div(out[i + c * N], diag);
-      out[i + c * N] = coeff;
-      for (int r = 0; r < i; ++r) out[r + c * N] = x_add(x_mul(-coeff, a[r + i * N]), out[r + c * N]);
-    }
-  return true;
-  }
-}
-
-// compute_row in the reference's order.  c[], up[] -> k[] = dC/dt of this cell.
-template <int N>
-__device__ void exact_row(const SpeciesConst* sc, double fe, double ue, double dz, const double* c, const double* up,
-                          double* k) {
-  double sum_kc = 0.0;
-#pragma unroll
-  for (int s = 0; s < N; ++s) sum_kc = x_add(sum_kc, x_mul(sc[s].K, c[s]));
-  const double denom = x_add(1.0, sum_kc);
-  const double denom2 = x_mul(denom, denom);
-  double mat[N * N], inv[N * N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    const double nb = sc[i].nbar, Ki = sc[i].K;
-#pragma unroll
-    for (int j = 0; j < N; ++j) {
-      double J;
-      if (i == j) {
-        const double num = x_mul(x_mul(nb, Ki), x_sub(denom, x_mul(Ki, c[i])));
-        J = x_add(sc[i].lambda, x_div(num, denom2));
-      } else {
-        const double num = x_mul(x_mul(x_mul(-nb, Ki), sc[j].K), c[i]);
-        J = x_div(num, denom2);
-      }
-      mat[i + j * N] = x_add((i == j) ? 1.0 : 0.0, x_mul(fe, J));
-    }
-  }
-  if (!exact_try_inverse<N>(mat, inv)) {  // identity fallback, langmuir_multi.rs:790-796
-#pragma unroll
-    for (int q = 0; q < N * N; ++q) inv[q] = ((q % N) == (q / N)) ? 1.0 : 0.0;
-  }
-  double grad[N], dv[N];
-#pragma unroll
-  for (int s = 0; s < N; ++s) grad[s] = x_div(x_sub(c[s], up[s]), dz);
-#pragma unroll
-  for (int i = 0; i < N; ++i) dv[i] = x_mul(inv[i], grad[0]);
-#pragma unroll
-  for (int j = 1; j < N; ++j)
-#pragma unroll
-    for (int i = 0; i < N; ++i) dv[i] = x_add(x_mul(inv[i + j * N], grad[j]), dv[i]);
-#pragma unroll
-  for (int s = 0; s < N; ++s) k[s] = x_mul(-ue, dv[s]);
-}
-
-// ------------------------------------------------------------------------------------------------
-// FAST: A = I + fe*M = diag(alpha) - p q^T built in registers, LU with partial pivoting applied to
-// rhs = (-ue/dz)*(c - up), back substitution.  k = A^-1 rhs.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long abs_bits(double v) {
-  return (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull;
-}
-
-// One elimination step with a compile-time pivot column I (template recursion instead of a loop:
-// every register index is a constant, so the matrix never falls back to local memory).
-template <int N, int I>
-__device__ __forceinline__ void lu_step(double (&a)[N][N], double (&b)[N], bool& singular) {
-  if constexpr (I + 1 < N) {
-    // Partial pivoting.  Cheap test first (integer pipe): can any row below hold a larger |entry|?
-    // High words only, '>=' so that ties in the high word are never missed.  The matrices are
-    // close to diagonally dominant, so the swap path below is almost never entered.
-    unsigned below = 0u;
-#pragma unroll
-    for (int r = I + 1; r < N; ++r) below = max(below, abs_hi(a[r][I]));
-    if (__any_sync(0xffffffffu, below >= abs_hi(a[I][I]))) {
-      // Exact path: compare-and-swap row I against every row below.  Afterwards
-      // |a[I][I]| = max_r |a[r][I]|: a valid partial pivot.
-#pragma unroll
-      for (int r = I + 1; r < N; ++r) {
-        const bool sw = abs_bits(a[r][I]) > abs_bits(a[I][I]);
-#pragma unroll
-        for (int q = I; q < N; ++q) {
-          const double t = a[I][q];
-          a[I][q] = sw ? a[r][q] : t;
-          a[r][q] = sw ? t : a[r][q];
-        }
-        const double t = b[I];
-        b[I] = sw ? b[r] : t;
-        b[r] = sw ? t : b[r];
-      }
-    }
-  }
-  singular |= (a[I][I] == 0.0);
-  const double rp = fast_rcp(a[I][I]);
-  a[I][I] = rp;  // keep the reciprocal for the back substitution
-#pragma unroll
-  for (int r = I + 1; r < N; ++r) {
-    const double l = a[r][I] * rp;
-#pragma unroll
-    for (int q = I + 1; q < N; ++q) a[r][q] = fma(-l, a[I][q], a[r][q]);
-    b[r] = fma(-l, b[I], b[r]);
-  }
-  if constexpr (I + 1 < N) lu_step<N, I + 1>(a, b, singular);
-}
-
-template <int N, int I>
-__device__ __forceinline__ void back_step(const double (&a)[N][N], const double (&b)[N], double* k) {
-  double s = b[I];
-#pragma unroll
-  for (int q = I + 1; q < N; ++q) s = fma(-a[I][q], k[q], s);
-  k[I] = s * a[I][I];
-  if constexpr (I > 0) back_step<N, I - 1>(a, b, k);
-}
-
-template <int N>
-__device__ __forceinline__ void fast_row(const SpeciesConst* sc, double fe, double cg, const double* c,
-                                         const double* up, double* k) {
-  (void)fe;
-  double S = 0.0;
-#pragma unroll
-  for (int s = 0; s < N; ++s) S = fma(sc[s].K, c[s], S);
-  const double D = 1.0 + S;
-  const double rD2 = fast_rcp(D * D);
-  const double DrD2 = D * rD2;
-  double a[N][N], b[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    const double p = sc[i].feNK * c[i] * rD2;  // fe * nbar_i K_i c_i / D^2
-#pragma unroll
-    for (int j = 0; j < N; ++j) a[i][j] = -p * sc[j].K;
-    a[i][i] = fma(sc[i].feNK, DrD2, sc[i].a0) + a[i][i];  // 1 + fe*(lambda_i + nbar_i K_i (D - K_i c_i)/D^2)
-    b[i] = (c[i] - up[i]) * cg;
-  }
-  bool singular = false;
-  lu_step<N, 0>(a, b, singular);
-  back_step<N, N - 1>(a, b, k);
-  if (singular) {  // exact zero pivot: the reference falls back to the identity (A^-1 := I)
-#pragma unroll
-    for (int s = 0; s < N; ++s) k[s] = (c[s] - up[s]) * cg;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// FAST dense, speculative form (the hot path for n <= 8).  Two changes against fast_row, same LU:
-//  * column scaling x_j = y_j / K_j:  (diag(alpha) - p q^T) x = r  <=>  (diag(alpha_i/K_i) - p 1^T) y = r,
-//    so the off-diagonal entries of row i are all -p_i (no n^2 products to build the matrix) and the
-//    scaling by cg = -ue/dz moves into the final product x_j = y_j * (cg / K_j).  Column scaling
-//    commutes with Gaussian elimination: the multipliers and the pivot ROWS are those of the unscaled
-//    matrix.
-//  * the elimination runs without row exchanges and without votes or branches (straight-line code the
-//    scheduler can overlap: reciprocal chain of step i+1 under the rank-1 update of step i) while the
-//    partial-pivoting test of every step is evaluated on the integer pipe; a cell where a row below the
-//    diagonal could hold a larger entry (or a pivot is exactly zero) returns true and is redone by the
-//    caller with the row-exchanging fast_row.  The matrices are close to diagonally dominant
-//    (|a_ri|/|a_ii| <= (nbar_r/nbar_i) K_r c_r / (1 + sum K c)), so this is rare.
-// ------------------------------------------------------------------------------------------------
-template <int N, int I>
-__device__ __forceinline__ void lu_step_spec(double (&a)[N][N], double (&b)[N], bool& redo) {
-  if constexpr (I + 1 < N) {
-    unsigned below = 0u;
-#pragma unroll
-    for (int r = I + 1; r < N; ++r) below = max(below, abs_hi(a[r][I]));
-    redo |= below >= abs_hi(a[I][I]);  // '>=' on the high words: never misses a needed exchange
-  }
-  redo |= (a[I][I] == 0.0);
-  const double rp = fast_rcp(a[I][I]);
-  a[I][I] = rp;
-#pragma unroll
-  for (int r = I + 1; r < N; ++r) {
-    const double l = a[r][I] * rp;
-#pragma unroll
-    for (int q = I + 1; q < N; ++q) a[r][q] = fma(-l, a[I][q], a[r][q]);
-    b[r] = fma(-l, b[I], b[r]);
-  }
-  if constexpr (I + 1 < N) lu_step_spec<N, I + 1>(a, b, redo);
-}
-
-template <int N>
-__device__ __forceinline__ bool fast_row_spec(const SpeciesConst* sc, const double* c, const double* up, double* k) {
-  double S0 = 0.0, S1 = 0.0;  // two chains: the sum is not on the critical path for long
-#pragma unroll
-  for (int s = 0; s < N; s += 2) {
-    S0 = fma(sc[s].K, c[s], S0);
-    if (s + 1 < N) S1 = fma(sc[s + 1].K, c[s + 1], S1);
-  }
-  const double D = 1.0 + (S0 + S1);
-  const double rD2 = fast_rcp(D * D);
-  const double DrD2 = D * rD2;
-  double a[N][N], b[N];
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    const double np = -(sc[i].feNK * (c[i] * rD2));  // -p_i = -fe nbar_i K_i c_i / D^2
-#pragma unroll
-    for (int j = 0; j < N; ++j) a[i][j] = np;
-    a[i][i] = fma(sc[i].feN, DrD2, sc[i].a0rK) + np;  // alpha_i / K_i - p_i
-    b[i] = c[i] - up[i];
-  }
-  bool redo = false;
-  lu_step_spec<N, 0>(a, b, redo);
-  back_step<N, N - 1>(a, b, k);
-#pragma unroll
-  for (int s = 0; s < N; ++s) k[s] *= sc[s].cgrK;
-  return redo;
-}
-
-// ------------------------------------------------------------------------------------------------
-// STRUCTURED: Gaussian elimination with partial pivoting on A = diag(alpha) - p q^T WITHOUT forming
-// the matrix.  Eliminating column i of diag(alpha) - g p q^T leaves diag(alpha') - g' p' q'^T on the
-// trailing block with g' = g * alpha_i / d_i, d_i = alpha_i - g p_i q_i (the pivot), so L, U and the
-// solve need O(n) scalars:  U[i][c] = -g_i p_i q_c,  L[r][i] = -g_i p_r q_i / d_i.
-// The pivot test of partial pivoting, |L[r][i] d_i| > |d_i| for some r > i, becomes
-// g_i q_i max_{r>i} |p_r| > |d_i|; when it fires the caller redoes the cell with the dense
-// row-exchanging LU (register LU for n <= 8, scratch-memory LU beyond).  Same pivots, same factors,
-// O(n) registers: this is what makes n > 8 fit a thread and lets two warps more per SM fly.
-// N > 0: compile-time n (registers); N == 0: runtime n (local arrays of kNMax).
-// ------------------------------------------------------------------------------------------------
-
-// Compile-time n: everything in registers, 4n doubles of state (K, p -> g*p, rhs -> x, suffix max ->
-// reciprocal pivot), two 128-bit shared loads of constants per species.  Reads the cell from shared
-// memory itself; the solution is left in x[].
-template <int N>
-__device__ __forceinline__ bool structured_cell(const SpeciesConst* sc, double cg, const double* SRC,
-                                                const double* inlet_row, uint32_t nz, uint32_t cc, double (&x)[N]) {
-  double K[N], pw[N], d[N];
-  double S = 0.0;
-#pragma unroll
-  for (int s = 0; s < N; ++s) {
-    const double c = SRC[(size_t)s * nz + cc];
-    const double up = (cc > 0) ? SRC[(size_t)s * nz + cc - 1] : inlet_row[s];
-    const double2 kf = *reinterpret_cast<const double2*>(&sc[s].K);  // {K, feNK}
-    K[s] = kf.x;
-    x[s] = (c - up) * cg;
-    S = fma(kf.x, c, S);
-    pw[s] = kf.y * c;  // feNK_s * c_s; p_s = pw_s / D^2
-  }
-  const double rD = fast_rcp(1.0 + S);
-  const double rD2 = rD * rD;
-  double sfx = 0.0;
-#pragma unroll
-  for (int s = N - 1; s >= 0; --s) {
-    d[s] = sfx * rD2;  // max_{r>s} |p_r|, parked until the forward sweep reaches s
-    sfx = fmax(sfx, fabs(pw[s]));
-  }
-  double g = 1.0, carry = 0.0;
-  bool redo = false;
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    const double2 af = *reinterpret_cast<const double2*>(&sc[i].a0);  // {a0, feNK}
-    const double alpha = fma(af.y, rD, af.x);                        // 1 + fe*(lambda_i + nbar_i K_i / D)
-    const double p = pw[i] * rD2;
-    const double b_i = fma(p, carry, x[i]);
-    const double t = g * p;
-    const double piv = fma(-t, K[i], alpha);
-    const double gq = g * K[i];
-    redo |= (gq * d[i] > fabs(piv)) || (piv == 0.0);
-    const double rp = fast_rcp(piv);
-    pw[i] = t;
-    x[i] = b_i;
-    d[i] = rp;
-    carry = fma(gq * rp, b_i, carry);
-    g = g * (alpha * rp);
-  }
-  double Sx = 0.0;
-#pragma unroll
-  for (int i = N - 1; i >= 0; --i) {
-    const double xi = fma(pw[i], Sx, x[i]) * d[i];
-    x[i] = xi;
-    Sx = fma(K[i], xi, Sx);
-  }
-  return redo;
-}
-
-// Runtime n (9 .. kNMax): the same sweep over local arrays.
-template <int N>
-__device__ __forceinline__ bool structured_row(int n_rt, const SpeciesConst* sc, double cg, const double* c,
-                                               const double* up, double* k) {
-  constexpr int CAP = N > 0 ? N : kNMax;
-  const int n = N > 0 ? N : n_rt;
-  double S = 0.0;
-#pragma unroll
-  for (int s = 0; s < CAP; ++s)
-    if (s < n) S = fma(sc[s].K, c[s], S);
-  const double rD = fast_rcp(1.0 + S);
-  const double rD2 = rD * rD;
-  double p[CAP], d[CAP], gp[CAP], bb[CAP];  // p_i, reciprocal pivots, g_i*p_i, eliminated rhs
-  double pmax_suffix = 0.0;
-#pragma unroll
-  for (int s = CAP - 1; s >= 0; --s)
-    if (s < n) {
-      p[s] = sc[s].feNK * c[s] * rD2;
-      d[s] = pmax_suffix;  // max_{r>s} |p_r| parked here until the forward sweep reaches s
-      pmax_suffix = fmax(pmax_suffix, fabs(p[s]));
-    }
-  double g = 1.0, carry = 0.0;
-  bool need_pivot = false, singular = false;
-#pragma unroll
-  for (int i = 0; i < CAP; ++i)
-    if (i < n) {
-      const double q = sc[i].K;
-      const double alpha = fma(sc[i].feNK, rD, sc[i].a0);  // 1 + fe*(lambda_i + nbar_i K_i / D)
-      const double b_i = fma(p[i], carry, (c[i] - up[i]) * cg);
-      const double t = g * p[i];
-      const double piv = fma(-t, q, alpha);
-      const double gq = g * q;
-      need_pivot |= (gq * d[i] > fabs(piv));
-      singular |= (piv == 0.0);
-      const double rp = fast_rcp(piv);
-      gp[i] = t;
-      bb[i] = b_i;
-      d[i] = rp;
-      const double w = gq * rp;
-      carry = fma(w, b_i, carry);
-      g = g * (alpha * rp);
-    }
-  double Sx = 0.0;
-#pragma unroll
-  for (int i = CAP - 1; i >= 0; --i)
-    if (i < n) {
-      const double x = fma(gp[i], Sx, bb[i]) * d[i];
-      k[i] = x;
-      Sx = fma(sc[i].K, x, Sx);
-    }
-  return need_pivot || singular;
-}
-
-// Dense LU with partial pivoting for runtime n, matrix in per-thread scratch memory
-// (element e of this thread at a[e * stride]).  FAST arithmetic; only reached when the structured
-// sweep reports that a row exchange is needed (or an exactly singular pivot: identity fallback).
-__device__ void dense_row_scratch(int n, const SpeciesConst* sc, double cg, const double* c, const double* up,
-                                  double* k, double* a, size_t stride) {
-  auto A = [&](int i, int j) -> double& { return a[((size_t)i * n + j) * stride]; };
-  double S = 0.0;
-  for (int s = 0; s < n; ++s) S = fma(sc[s].K, c[s], S);
-  const double D = 1.0 + S, rD2 = 1.0 / (D * D);
-  for (int i = 0; i < n; ++i) {
-    const double p = sc[i].feNK * c[i] * rD2;
-    for (int j = 0; j < n; ++j) A(i, j) = -p * sc[j].K;
-    A(i, i) = fma(sc[i].feNK, D * rD2, sc[i].a0) + A(i, i);
-    k[i] = (c[i] - up[i]) * cg;
-  }
-  bool singular = false;
-  for (int i = 0; i < n; ++i) {
-    int piv = i;
-    double best = fabs(A(i, i));
-    for (int r = i + 1; r < n; ++r)
-      if (fabs(A(r, i)) > best) {
-        best = fabs(A(r, i));
-        piv = r;
-      }
-    if (piv != i) {
-      for (int q = i; q < n; ++q) {
-        const double t = A(i, q);
-        A(i, q) = A(piv, q);
-        A(piv, q) = t;
-      }
-      const double t = k[i];
-      k[i] = k[piv];
-      k[piv] = t;
-    }
-    singular |= (A(i, i) == 0.0);
-    const double rp = 1.0 / A(i, i);
-    for (int r = i + 1; r < n; ++r) {
-      const double l = A(r, i) * rp;
-      for (int q = i + 1; q < n; ++q) A(r, q) = fma(-l, A(i, q), A(r, q));
-      k[r] = fma(-l, k[i], k[r]);
-    }
-  }
-  for (int i = n - 1; i >= 0; --i) {
-    double s = k[i];
-    for (int q = i + 1; q < n; ++q) s = fma(-A(i, q), k[q], s);
-    k[i] = s / A(i, i);
-  }
-  if (singular)
-    for (int s = 0; s < n; ++s) k[s] = (c[s] - up[s]) * cg;
-}
-
-// EXACT for runtime n >= 5: compute_row with nalgebra's lu::try_invert_to and gemv, matrices in
-// per-thread scratch (mat, inverse, LU copy: 3 n^2 doubles).  Same operation order as exact_row<N>.
-__device__ void exact_row_scratch(int n, const SpeciesConst* sc, double fe, double ue, double dz, const double* c,
-                                  const double* up, double* k, double* scratch, size_t stride) {
-  const size_t nn = (size_t)n * n;
-  auto M = [&](int i, int j) -> double& { return scratch[((size_t)i + (size_t)j * n) * stride]; };             // mat
-  auto O = [&](int i, int j) -> double& { return scratch[(nn + (size_t)i + (size_t)j * n) * stride]; };        // inverse
-  auto A = [&](int i, int j) -> double& { return scratch[(2 * nn + (size_t)i + (size_t)j * n) * stride]; };    // LU copy
-  double sum_kc = 0.0;
-  for (int s = 0; s < n; ++s) sum_kc = x_add(sum_kc, x_mul(sc[s].K, c[s]));
-  const double denom = x_add(1.0, sum_kc);
-  const double denom2 = x_mul(denom, denom);
-  for (int i = 0; i < n; ++i) {
-    const double nb = sc[i].nbar, Ki = sc[i].K;
-    for (int j = 0; j < n; ++j) {
-      double J;
-      if (i == j) {
-        const double num = x_mul(x_mul(nb, Ki), x_sub(denom, x_mul(Ki, c[i])));
-        J = x_add(sc[i].lambda, x_div(num, denom2));
-      } else {
-        const double num = x_mul(x_mul(x_mul(-nb, Ki), sc[j].K), c[i]);
-        J = x_div(num, denom2);
-      }
-      M(i, j) = x_add((i == j) ? 1.0 : 0.0, x_mul(fe, J));
-    }
-  }
-  // lu::try_invert_to
-  bool ok = true;
-  for (int j = 0; j < n; ++j)
-    for (int i = 0; i < n; ++i) {
-      A(i, j) = M(i, j);
-      O(i, j) = (i == j) ? 1.0 : 0.0;
-    }
-  for (int i = 0; i < n && ok; ++i) {
-    int piv = i;
-    double the_max = fabs(A(i, i));
-    for (int r = i + 1; r < n; ++r) {
-      const double v = fabs(A(r, i));
-      if (v > the_max) {
-        the_max = v;
-        piv = r;
-      }
-    }
-    const double diag = A(piv, i);
-    if (diag == 0.0) {
-      ok = false;
-      break;
-    }
-    if (piv != i) {
-      for (int j = 0; j < n; ++j) {
-        const double t = O(i, j);
-        O(i, j) = O(piv, j);
-        O(piv, j) = t;
-      }
-      for (int j = 0; j <= i; ++j) {
-        const double t = A(i, j);
-        A(i, j) = A(piv, j);
-        A(piv, j) = t;
-      }
-    }
-    const double inv_diag = x_div(1.0, diag);
-    for (int r = i + 1; r < n; ++r) A(r, i) = x_mul(A(r, i), inv_diag);
-    for (int q = i + 1; q < n; ++q) {
-      if (piv != i) {
-        const double t = A(i, q);
-        A(i, q) = A(piv, q);
-        A(piv, q) = t;
-      }
-      const double neg_pivot = -A(i, q);
-      for (int r = i + 1; r < n; ++r) A(r, q) = x_add(x_mul(neg_pivot, A(r, i)), A(r, q));
-    }
-  }
-  if (ok) {
-    for (int cc = 0; cc < n; ++cc)
-      for (int i = 0; i + 1 < n; ++i) {
-        const double coeff = O(i, cc);
-        for (int r = i + 1; r < n; ++r) O(r, cc) = x_add(x_mul(-coeff, A(r, i)), O(r, cc));
-      }
-    for (int cc = 0; cc < n && ok; ++cc)
-      for (int i = n - 1; i >= 0; --i) {
-        const double diag = A(i, i);
-        if (diag == 0.0) {
-          ok = false;
-          break;
-        }
-        const double coeff = x_div(O(i, cc), diag);
-        O(i, cc) = coeff;
-        for (int r = 0; r < i; ++r) O(r, cc) = x_add(x_mul(-coeff, A(r, i)), O(r, cc));
-      }
-  }
-  if (!ok)  // identity fallback, langmuir_multi.rs:790-796
-    for (int j = 0; j < n; ++j)
-      for (int i = 0; i < n; ++i) O(i, j) = (i == j) ? 1.0 : 0.0;
-  // grad, gemv (column by column, j ascending), scale
-  for (int i = 0; i < n; ++i) k[i] = x_mul(O(i, 0), x_div(x_sub(c[0], up[0]), dz));
-  for (int j = 1; j < n; ++j) {
-    const double gj = x_div(x_sub(c[j], up[j]), dz);
-    for (int i = 0; i < n; ++i) k[i] = x_add(x_mul(O(i, j), gj), k[i]);
-  }
-  for (int s = 0; s < n; ++s) k[s] = x_mul(-ue, k[s]);
-}
-
-// Stage algebra of one cell (all species) on the shared-memory state.  Returns the non-finite flag of
-// the new state where the stage produces one.
-struct StageCtx {
-  double* Y;
-  double* ACC;
-  double* DST;
-  uint32_t nz;
-  int stage;  // 0 Euler, 1..4 RK4
-  double dt, h2, h6;
-};
-
-template <int N, bool EXACT>
-__device__ __forceinline__ bool apply_stage(const StageCtx& st, uint32_t cc, const double* k, int n_rt) {
-  constexpr int CAP = N > 0 ? N : kNMaxDecl;
-  const int n = N > 0 ? N : n_rt;
-  auto axpy = [](double y, double kk, double h) { return EXACT ? x_add(y, x_mul(kk, h)) : fma(kk, h, y); };
-  bool bad = false;
-#pragma unroll
-  for (int s = 0; s < CAP; ++s)
-    if (s < n) {
-      const size_t idx = (size_t)s * st.nz + cc;
-      if (st.stage == 0) {
-        const double yn = axpy(st.Y[idx], k[s], st.dt);
-        st.Y[idx] = yn;  // Euler reads SRC = U0/U1 (a copy of Y), so Y can be overwritten
-        st.DST[idx] = yn;
-        bad |= hi_nonfinite(abs_hi(yn));
-      } else if (st.stage == 1) {
-        st.ACC[idx] = k[s];
-        st.DST[idx] = axpy(st.Y[idx], k[s], st.h2);
-      } else if (st.stage == 2) {
-        st.ACC[idx] = axpy(st.ACC[idx], k[s], 2.0);
-        st.DST[idx] = axpy(st.Y[idx], k[s], st.h2);
-      } else if (st.stage == 3) {
-        st.ACC[idx] = axpy(st.ACC[idx], k[s], 2.0);
-        st.DST[idx] = axpy(st.Y[idx], k[s], st.dt);
-      } else {
-        const double w = EXACT ? x_add(st.ACC[idx], k[s]) : st.ACC[idx] + k[s];
-        const double yn = axpy(st.Y[idx], w, st.h6);
-        st.Y[idx] = yn;
-        bad |= hi_nonfinite(abs_hi(yn));
-      }
-    }
-  return bad;
-}
-
-// The dense fallback of the structured kernels, kept out of line so that its 64-entry matrix does not
-// raise the register count of the hot path (it reloads the cell from shared memory itself).
-template <int N>
-__device__ __noinline__ bool cold_cell(const SpeciesConst* sc, double fe, double cg, const double* SRC,
-                                       const double* inlet_row, uint32_t cc, bool write, StageCtx st) {
-  double c[N], up[N], k[N];
-#pragma unroll
-  for (int s = 0; s < N; ++s) {
-    c[s] = SRC[(size_t)s * st.nz + cc];
-    up[s] = (cc > 0) ? SRC[(size_t)s * st.nz + cc - 1] : inlet_row[s];
-  }
-  fast_row<N>(sc, fe, cg, c, up, k);  // warp-synchronous inside (pivot votes): called by whole warps
-  return write ? apply_stage<N, false>(st, cc, k, N) : false;
-}
-
-// ---- kernel ---------------------------------------------------------------------------------------
-// ARITH: CHROM_ARITH_FAST (dense register LU, N <= 8), CHROM_ARITH_EXACT, CHROM_KARITH_STRUCT.
-// N == 0: runtime n = b.n_species (9 .. kNMax); EXACT and STRUCT only.
 constexpr int multi_max_threads(int N, int ARITH) {
   return (ARITH == CHROM_KARITH_STRUCT && N > 0) ? 512 : ((N > 0 && N <= 2) ? 512 : 256);
 }
 
-template <int N, int METHOD, int ARITH>
-__global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_resident(const BatchDev b, double* scratch) {
-  constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
-  constexpr bool EXACT = (ARITH == CHROM_ARITH_EXACT);
-  constexpr int CAP = N > 0 ? N : kNMax;
-  extern __shared__ double smem[];
-  const int n = N > 0 ? N : (int)b.n_species;
-  const uint32_t nz = b.nz;
-  const int T = blockDim.x;
-  const int tid = threadIdx.x;
-  const size_t plane = (size_t)n * nz;  // doubles per state array
-  double* Y = smem;
-  double* ACC = Y + plane;
-  double* U0 = ACC + plane;
-  double* U1 = U0 + plane;
-  double* inlet = U1 + plane;                        // [3][n] current step's inlet values
-  double* summ = inlet + 3 * n;                      // [n][5]: area, moment, max, tmax, v_prev
-  SpeciesConst* sc = (SpeciesConst*)(summ + 5 * n);  // [n]
-  __shared__ const double* tabs[CAP];
-  // per-thread scratch (runtime-n dense paths): element e of this thread at my_scratch[e * sstride]
-  const size_t sstride = (size_t)gridDim.x * T;
-  double* my_scratch = scratch ? scratch + (size_t)blockIdx.x * T + tid : nullptr;
-
-  const double dt = b.dt, h2 = b.half_dt, h6 = b.sixth_dt;
-  const uint32_t steps = b.steps;
-  const int cpt = (int)((nz + T - 1) / T);  // cells per thread
-  auto axpy = [](double y, double k, double h) { return EXACT ? x_add(y, x_mul(k, h)) : fma(k, h, y); };
-
-  for (uint32_t col = blockIdx.x; col < b.n_cols; col += gridDim.x) {  // persistent CTAs over columns
-    const chrom_multi_col cp = b.mcols[col];
-    const double fe = cp.fe, ue = cp.ue, dz = cp.dz;
-    const double cg = -ue / dz;  // FAST only
-    __syncthreads();             // the previous column's readers of sc / tabs / Y are done
-    for (int s = tid; s < n; s += T) {
-      const chrom_species sp = b.species[cp.species_off + s];
-      SpeciesConst q;
-      q.lambda = sp.lambda;
-      q.K = sp.langmuir_k;
-      q.nbar = EXACT ? x_mul(cp.stationary_fraction, (double)sp.port_number)
-                     : cp.stationary_fraction * (double)sp.port_number;
-      q.a0 = 1.0 + fe * sp.lambda;
-      q.feNK = fe * (q.nbar * sp.langmuir_k);
-      q.feNK2 = q.feNK;
-      q.a0rK = q.a0 / sp.langmuir_k;
-      q.feN = fe * q.nbar;
-      q.cgrK = cg / sp.langmuir_k;
-      q.pad_ = 0.0;
-      sc[s] = q;
-      tabs[s] = b.tables + (size_t)sp.inj_table * b.steps * ST;
-    }
-    for (size_t i = tid; i < plane; i += T) {
-      Y[i] = b.y0 ? b.y0[(size_t)col * plane + i] : 0.0;
-      ACC[i] = 0.0;
-    }
-    __syncthreads();
-
-    // initial samples
-    for (int s = tid; s < n; s += T) {
-      const double v0 = Y[(size_t)s * nz + nz - 1];
-      if (b.outlet) b.outlet[((size_t)col * n + s) * b.n_out] = v0;
-      summ[s * 5 + 0] = 0.0;
-      summ[s * 5 + 1] = 0.0;
-      summ[s * 5 + 2] = v0;
-      summ[s * 5 + 3] = 0.0;
-      summ[s * 5 + 4] = v0;
-    }
-    if (b.snapshots)
-      for (size_t i = tid; i < plane; i += T) b.snapshots[(size_t)col * b.n_snap * plane + i] = Y[i];
-    uint32_t out_count = b.outlet_stride, snap_count = b.snapshot_stride, out_slot = 1, snap_slot = 1;
-    bool done = false;
-
-    // One stage: K = f(SRC, inlet row `irow`), then the stage algebra selected by `stage`.
-    auto run_stage = [&](const double* SRC, double* DST, int irow, int stage) -> bool {
-      bool bad = false;
-      StageCtx st{Y, ACC, DST, nz, METHOD == CHROM_EULER ? 0 : stage, dt, h2, h6};
-      unsigned redo_mask = 0u;  // structured kernels: cells whose LU needs a row exchange
-      for (int ci = 0; ci < cpt; ++ci) {
-        const uint32_t cell = (uint32_t)tid + (uint32_t)ci * T;
-        const bool live = cell < nz;
-        const uint32_t cc = live ? cell : nz - 1;  // idle lanes recompute the last cell, never store
-        double k[CAP];
-        if constexpr (ARITH == CHROM_KARITH_STRUCT && N > 0) {
-          const bool redo = structured_cell<N>(sc, cg, SRC, inlet + irow * n, nz, cc, k);
-          if (redo) redo_mask |= 1u << ci;
-          else if (live) bad |= apply_stage<N, false>(st, cc, k, n);
-        } else {
-          double c[CAP], up[CAP];
-#pragma unroll
-          for (int s = 0; s < CAP; ++s)
-            if (s < n) {
-              c[s] = SRC[(size_t)s * nz + cc];
-              up[s] = (cc > 0) ? SRC[(size_t)s * nz + cc - 1] : inlet[irow * n + s];
-            }
-          if constexpr (EXACT) {
-            if constexpr (N > 0) exact_row<N>(sc, fe, ue, dz, c, up, k);
-            else exact_row_scratch(n, sc, fe, ue, dz, c, up, k, my_scratch, sstride);
-          } else if constexpr (ARITH == CHROM_KARITH_STRUCT) {
-            if (structured_row<0>(n, sc, cg, c, up, k)) dense_row_scratch(n, sc, cg, c, up, k, my_scratch, sstride);
-          } else {
-            // speculative exchange-free LU; a warp with a flagged cell redoes it with the row-exchanging LU
-            constexpr int NN = N > 0 ? N : 1;
-            const bool redo = fast_row_spec<NN>(sc, c, up, k);
-            if (__any_sync(0xffffffffu, redo)) {
-              bad |= cold_cell<NN>(sc, fe, cg, SRC, inlet + irow * n, cc, live, st);
-              continue;
-            }
-          }
-          if (live) bad |= apply_stage<N, EXACT>(st, cc, k, n);
-        }
-      }
-      if constexpr (ARITH == CHROM_KARITH_STRUCT && N > 0) {
-        // cold pass: redo the flagged cells with the dense row-exchanging LU (whole warps, out of line)
-        if (__any_sync(0xffffffffu, redo_mask != 0u)) {
-          for (int ci = 0; ci < cpt; ++ci) {
-            const bool mine = (redo_mask >> ci) & 1u;
-            if (!__any_sync(0xffffffffu, mine)) continue;
-            const uint32_t cell = (uint32_t)tid + (uint32_t)ci * T;
-            const bool live = cell < nz;
-            bad |= cold_cell<(N > 0 ? N : 1)>(sc, fe, cg, SRC, inlet + irow * n, live ? cell : nz - 1, mine && live, st);
-          }
-        }
-      }
-      return bad;
-    };
-
-    if (METHOD == CHROM_EULER) {
-      for (size_t i = tid; i < plane; i += T) U0[i] = Y[i];
-    }
-
-    for (uint32_t step = 0; step < steps; ++step) {
-      for (int i = tid; i < n * ST; i += T) {  // inlet values of this step: [stage row][species]
-        const int s = i % n, r = i / n;
-        inlet[r * n + s] = tabs[s][(size_t)step * ST + r];
-      }
-      __syncthreads();
-      bool bad;
-      if (METHOD == CHROM_RK4) {
-        run_stage(Y, U0, 0, 1);
-        __syncthreads();
-        run_stage(U0, U1, 1, 2);
-        __syncthreads();
-        run_stage(U1, U0, 1, 3);
-        __syncthreads();
-        bad = run_stage(U0, nullptr, 2, 4);
-      } else {
-        // ping-pong: even steps read U0 / write U1, odd steps the reverse; Y always holds the new state
-        bad = (step & 1u) ? run_stage(U1, U0, 0, 0) : run_stage(U0, U1, 0, 0);
-      }
-      const int any_bad = __syncthreads_or(bad);
-
-      // ---- samples --------------------------------------------------------------------------
-      const bool out_now = b.outlet && (--out_count == 0);
-      if (out_now) out_count = b.outlet_stride;
-      for (int s = tid; s < n; s += T) {
-        const double v = Y[(size_t)s * nz + nz - 1];
-        if (out_now) b.outlet[((size_t)col * n + s) * b.n_out + out_slot] = v;
-        if (b.summary) {
-          const double t0 = (double)step * dt, t1 = ((double)step + 1.0) * dt;
-          const double w = 0.5 * (t1 - t0);
-          double* sm = summ + s * 5;
-          sm[0] = fma(w, sm[4] + v, sm[0]);
-          sm[1] = fma(w, fma(t0, sm[4], t1 * v), sm[1]);
-          if (v > sm[2]) {
-            sm[2] = v;
-            sm[3] = t1;
-          }
-          sm[4] = v;
-        }
-      }
-      if (out_now) ++out_slot;
-      if (b.snapshots && --snap_count == 0) {
-        snap_count = b.snapshot_stride;
-        double* dst = b.snapshots + ((size_t)col * b.n_snap + snap_slot) * plane;
-        for (size_t i = tid; i < plane; i += T) dst[i] = Y[i];
-        ++snap_slot;
-      }
-      if (any_bad && !done) {  // validate_state: NaN anywhere wins over Inf (solver/mod.rs:519-548)
-        bool has_nan = false;
-        for (size_t i = tid; i < plane; i += T) has_nan |= (Y[i] != Y[i]);
-        const int any_nan = __syncthreads_or(has_nan);
-        if (tid == 0 && b.status) b.status[col] = any_nan ? (long long)(step + 1) : -(long long)(step + 1);
-        done = true;
-      }
-    }
-    __syncthreads();
-    if (b.final_state)
-      for (size_t i = tid; i < plane; i += T) b.final_state[(size_t)col * plane + i] = Y[i];
-    if (b.summary)
-      for (int s = tid; s < n; s += T) {
-        double* o = b.summary + ((size_t)col * n + s) * 4;
-        const double* sm = summ + s * 5;
-        o[0] = sm[0];
-        o[1] = (sm[0] != 0.0) ? sm[1] / sm[0] : 0.0;
-        o[2] = sm[2];
-        o[3] = sm[3];
-      }
-  }
-}
-
-typedef void (*mkern_t)(const BatchDev, double*);
-
-template <int N>
-mkern_t pick_n(int method, int arith) {
-  if (method == CHROM_RK4) {
-    if (arith == CHROM_ARITH_EXACT) return k_multi_resident<N, CHROM_RK4, CHROM_ARITH_EXACT>;
-    if (arith == CHROM_KARITH_STRUCT) return k_multi_resident<N, CHROM_RK4, CHROM_KARITH_STRUCT>;
-    return N > 0 ? k_multi_resident<(N > 0 ? N : 1), CHROM_RK4, CHROM_ARITH_FAST> : nullptr;
-  }
-  if (arith == CHROM_ARITH_EXACT) return k_multi_resident<N, CHROM_EULER, CHROM_ARITH_EXACT>;
-  if (arith == CHROM_KARITH_STRUCT) return k_multi_resident<N, CHROM_EULER, CHROM_KARITH_STRUCT>;
-  return N > 0 ? k_multi_resident<(N > 0 ? N : 1), CHROM_EULER, CHROM_ARITH_FAST> : nullptr;
-}
-
 mkern_t lookup_multi(int n, int method, int arith) {
   switch (n) {
-    case 1: return pick_n<1>(method, arith);
-    case 2: return pick_n<2>(method, arith);
-    case 3: return pick_n<3>(method, arith);
-    case 4: return pick_n<4>(method, arith);
-    case 5: return pick_n<5>(method, arith);
-    case 6: return pick_n<6>(method, arith);
-    case 7: return pick_n<7>(method, arith);
-    case 8: return pick_n<8>(method, arith);
+    case 1: return multi_pick_1(method, arith);
+    case 2: return multi_pick_2(method, arith);
+    case 3: return multi_pick_3(method, arith);
+    case 4: return multi_pick_4(method, arith);
+    case 5: return multi_pick_5(method, arith);
+    case 6: return multi_pick_6(method, arith);
+    case 7: return multi_pick_7(method, arith);
+    case 8: return multi_pick_8(method, arith);
   }
-  return (n >= 9 && n <= kNMax) ? pick_n<0>(method, arith) : nullptr;
+  return (n >= 9 && n <= kNMax) ? multi_pick_0(method, arith) : nullptr;
 }
 
 size_t multi_smem_bytes(int n, uint32_t nz) {
-  return ((size_t)4 * n * nz + 3 * n + 5 * n) * sizeof(double) + (size_t)n * sizeof(SpeciesConst);
+  return ((size_t)4 * n * nz + 3 * n + 5 * n) * sizeof(double) + (size_t)n * kSpeciesConstBytes;
 }
 
 }  // namespace
