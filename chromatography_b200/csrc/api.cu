@@ -276,11 +276,23 @@ int32_t build_shard(chrom_cuda_plan* plan, Shard& sh, const chrom_single_col* sc
     }
   } else {
     b.arith = multi_kernel_arith((int)cfg.n_species, cfg.arith);
-    ok = multi_resident_choose(b, d.sm_count, &sh.g, &why);
+    const char* force_tiled = getenv("CHROM_MULTI_TILED");  // experiments / tests: tiles even when the column fits
+    ok = !(force_tiled && atoi(force_tiled) != 0) && multi_resident_choose(b, d.sm_count, &sh.g, &why);
     if (ok) {
       const size_t per_thread = multi_scratch_per_thread((int)cfg.n_species, b.arith);
       if (per_thread) {
         CUDA_TRY(ctx, sh.scratch.alloc(per_thread * sh.g.grid.x * sh.g.block.x, d.stream));
+        b.scratch = sh.scratch.p;
+      }
+    } else if ((ok = multi_tiled_choose(b, d.sm_count, &sh.g, &why))) {
+      // long columns / many species: the state streams through HBM/L2 in tiles (multi_tiled.cu)
+      CUDA_TRY(ctx, sh.ping.alloc(sh.n_cols * state_len, d.stream));
+      CUDA_TRY(ctx, sh.pong.alloc(sh.n_cols * (state_len + multi_tiled_extra_doubles(cfg.n_species)), d.stream));
+      b.ping = sh.ping.p;
+      b.pong = sh.pong.p;
+      const size_t scratch = multi_tiled_scratch_doubles(b, sh.g);
+      if (scratch) {
+        CUDA_TRY(ctx, sh.scratch.alloc(scratch, d.stream));
         b.scratch = sh.scratch.p;
       }
     }
@@ -381,8 +393,10 @@ int32_t launch_batch(chrom_cuda_ctx* ctx, const BatchDev& b, const LaunchGeom& g
       e = single_stream_launch(b, g, s);
       break;
     case 4:
-    case 5:
       e = multi_resident_launch(b, g, s);
+      break;
+    case 5:
+      e = multi_tiled_launch(b, g, s);
       break;
     default:
       return fail(ctx, CHROM_ERR_UNSUPPORTED, "plan has no kernel");
@@ -578,8 +592,8 @@ int32_t chrom_cuda_plan_execute(chrom_cuda_plan* plan) {
     CUDA_TRY(ctx, cudaSetDevice(d.id));
     CUDA_TRY(ctx, cudaMemsetAsync(sh->status.p, 0, sh->n_cols * sizeof(long long), d.stream));
     CUDA_TRY(ctx, cudaEventRecord(d.ev[2], d.stream));
-    if (sh->g.kind == 3) {
-      // one launch per time step: replay them as a CUDA graph (captured on first use)
+    if (sh->g.kind == 3 || (sh->g.kind == 5 && sh->g.launches_per_execute > 3)) {
+      // one launch per (few) time step(s): replay them as a CUDA graph (captured on first use)
       if (!sh->graph) {
         cudaGraph_t graph = nullptr;
         CUDA_TRY(ctx, cudaStreamBeginCapture(d.stream, cudaStreamCaptureModeThreadLocal));

@@ -44,9 +44,19 @@ struct BatchDev {
   double dt, half_dt, sixth_dt;  // dt, dt/2.0, dt/6.0 evaluated on the host in IEEE double
 };
 
+// Per-launch arguments of the tiled LangmuirMulti kernels (multi_tiled.cuh).
+struct TiledArgs {
+  const double* src;          // [n_cols][n][nz] state at step0
+  double* dst;                // [n_cols][n][nz] state at step0 + nsub
+  unsigned long long* code;   // [n_cols] ~0 = clean, else (step << 1) | (NaN ? 0 : 1), merged with atomicMin
+  double* gsumm;              // [n_cols][n][5] running summary (area, moment, max, tmax, previous sample)
+  uint32_t step0, nsub;       // this launch advances steps step0 .. step0 + nsub - 1
+  uint32_t tiles_per_col, tw, halo, pitch;  // tile width (cells), upstream halo, shared-memory row pitch (odd)
+};
+
 // How a kernel family maps a batch onto the machine; filled by the *_choose functions.
 struct LaunchGeom {
-  int kind = 0;           // 1 single_resident, 2 single_resident_mw, 3 single_stream, 4 multi_resident, 5 multi_warp
+  int kind = 0;           // 1 single_resident, 2 single_resident_mw, 3 single_stream, 4 multi_resident, 5 multi_tiled
   int M = 0;              // cells per lane
   int L = 0;              // lanes per column (resident) / threads per column
   int cpw = 0;            // columns per warp (resident, single warp)
@@ -55,6 +65,9 @@ struct LaunchGeom {
   size_t smem = 0;
   uint64_t launches_per_execute = 1;
   uint32_t cols_per_wave = 0;  // columns one full wave of CTAs covers (0: the path is not chunkable)
+  // multi_tiled: tile width, halo, shared-memory pitch, steps per launch, species per lane (0 = thread per cell)
+  uint32_t tw = 0, halo = 0, pitch = 0, nsub = 0;
+  int wj = 0;
   std::string name;
 };
 
@@ -72,6 +85,12 @@ bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::
 cudaError_t multi_resident_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s);
 int multi_kernel_arith(int n_species, int arith);
 size_t multi_scratch_per_thread(int n_species, int kernel_arith);
+
+// multi_tiled.cu — LangmuirMulti beyond the resident capacity (long columns, n > 64): tiles through HBM/L2
+bool multi_tiled_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why);
+cudaError_t multi_tiled_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s);
+size_t multi_tiled_extra_doubles(uint32_t n_species);  // per column, behind the pong buffer: status code + summary
+size_t multi_tiled_scratch_doubles(const BatchDev& b, const LaunchGeom& g);
 
 // probe.cu
 cudaError_t measure_fp64_peak(int sm_count, cudaStream_t s, double* tflops, double* ms);

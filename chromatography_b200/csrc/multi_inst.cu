@@ -1,11 +1,24 @@
 // multi_inst.cu — one translation unit per species count (compiled with -DCHROM_MULTI_N=0..8, 0 = runtime n)
-// so that the nine instantiation sets of multi_kernels.cuh build in parallel.
-#include "multi_kernels.cuh"
+// so that the nine instantiation sets of multi_kernels.cuh / multi_tiled.cuh build in parallel.
+#include "multi_tiled.cuh"
 
 #define CHROM_CAT2(a, b) a##b
 #define CHROM_CAT(a, b) CHROM_CAT2(a, b)
 
 namespace chrom {
 typedef void (*mkern_t)(const BatchDev, double*);
+typedef void (*tkern_t)(const BatchDev, double*, const TiledArgs);
 mkern_t CHROM_CAT(multi_pick_, CHROM_MULTI_N)(int method, int arith) { return pick_n<CHROM_MULTI_N>(method, arith); }
+tkern_t CHROM_CAT(multi_tiled_pick_, CHROM_MULTI_N)(int method, int arith, int wj) {
+  return pick_tiled_n<CHROM_MULTI_N>(method, arith, wj);
+}
+#if CHROM_MULTI_N == 0
+void multi_tiled_init_launch(const BatchDev& b, double* ping, unsigned long long* code, cudaStream_t s) {
+  k_tiled_init<<<296, 256, 0, s>>>(b, ping, code);
+}
+void multi_tiled_finalize_launch(const BatchDev& b, const unsigned long long* code, const double* gsumm, cudaStream_t s) {
+  const uint32_t items = b.n_cols * b.n_species;
+  k_tiled_finalize<<<(items + 127) / 128, 128, 0, s>>>(b, code, gsumm);
+}
+#endif
 }  // namespace chrom
