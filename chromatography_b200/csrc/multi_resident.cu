@@ -72,6 +72,13 @@ bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::
     if (why) *why = "n_species outside 1..64";
     return false;
   }
+  if (n > 8) {  // the warp-per-cell kernels of multi_tiled.cu are faster; the runtime-n kernels here are opt-in
+    const char* e = getenv("CHROM_MULTI_THREAD_CELL");
+    if (!(e && atoi(e) != 0)) {
+      if (why) *why = "n_species > 8 runs one warp per cell (multi_tiled)";
+      return false;
+    }
+  }
   const size_t smem = multi_smem_bytes(n, b.nz);
   if (smem > 227u * 1024u) {
     if (why) *why = "nz * n_species exceeds the shared-memory-resident capacity (4*n*nz doubles <= 227 KB)";

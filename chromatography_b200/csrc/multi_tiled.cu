@@ -66,7 +66,7 @@ size_t multi_tiled_scratch_doubles(const BatchDev& b, const LaunchGeom& g) {
   return multi_scratch_per_thread((int)n, b.arith) * g.grid.x * g.block.x;
 }
 
-// Environment knobs (experiments and tests): CHROM_TILED_WARP=1 warp per cell also for n <= 64,
+// Environment knobs (experiments and tests): CHROM_TILED_WARP=1 warp per cell also for n = 5..8,
 // CHROM_TILED_TW=<cells> caps the tile width, CHROM_TILED_FUSE=<steps> sets the steps per launch.
 bool multi_tiled_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why) {
   const int n = (int)b.n_species;
@@ -76,12 +76,15 @@ bool multi_tiled_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::str
   }
   const bool rk4 = b.method == CHROM_RK4;
   int wj = 0;
-  // n <= 4 always runs thread per cell: nalgebra inverts those with closed forms, which are per-thread code
-  if (n > kThreadCellNMax || (n >= 5 && env_int("CHROM_TILED_WARP", 0) != 0))
-    wj = n <= 32 ? 1 : (n <= 64 ? 2 : (n <= 128 ? 4 : 8));
+  // n <= 8: thread per cell with the matrix in registers (n <= 4 always: nalgebra inverts those with closed
+  // forms, which are per-thread code).  n >= 9: warp per cell — measured 3-7x faster than the runtime-n
+  // thread-per-cell kernels (n = 12..64, FAST) and 1.2-6x in EXACT mode; CHROM_MULTI_THREAD_CELL=1 opts back.
+  const bool thread_cell = n <= 8 ? !(n >= 5 && env_int("CHROM_TILED_WARP", 0) != 0)
+                                  : (n <= kThreadCellNMax && env_int("CHROM_MULTI_THREAD_CELL", 0) != 0);
+  if (!thread_cell) wj = n <= 32 ? 1 : (n <= 64 ? 2 : (n <= 128 ? 4 : 8));
   const int karith = b.arith;
   int T;
-  if (wj > 0) T = 256;
+  if (wj > 0) T = (karith != CHROM_ARITH_EXACT && wj <= 2) ? 512 : 256;
   else T = (n <= 8) ? ((karith == CHROM_KARITH_STRUCT || n <= 2) ? 512 : 256) : 256;
   // widest tile that fits shared memory
   uint32_t tw_max = 0;
@@ -122,7 +125,9 @@ bool multi_tiled_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::str
     const uint32_t cpt = (tw + T - 1) / T;
     T = (int)(((tw + cpt - 1) / cpt + 31u) / 32u * 32u);
   } else {
-    T = (int)std::min<uint32_t>(256u, (tw + 0u) * 32u);
+    const uint32_t tmax = (karith != CHROM_ARITH_EXACT && wj <= 2) ? 512u : 256u;  // tiled_warp_threads (multi_tiled.cuh)
+    const uint32_t cells_per_pass = (karith != CHROM_ARITH_EXACT) ? (wj == 1 ? 4u : (wj == 2 ? 2u : 1u)) : 1u;
+    T = (int)std::min<uint32_t>(tmax, (tw + cells_per_pass - 1) / cells_per_pass * 32u);
     T = std::max(32, T / 32 * 32);
   }
   const uint32_t pitch = tw | 1u;

@@ -145,64 +145,101 @@ __device__ __noinline__ void warp_dense_fast(int n, const SpeciesConst* sc, doub
 
 // ---- warp per cell, FAST: the structured elimination as scans ------------------------------------------
 // Lane `lane` holds species lane + 32*j, j < WJ.  K/feNK/a0 are the lane's species constants (cached in
-// registers for the whole tile).  Returns true when partial pivoting would exchange rows (k[] invalid).
-template <int WJ>
-__device__ __forceinline__ bool warp_cell_fast(int n, int lane, const double (&K)[WJ], const double (&feNK)[WJ],
-                                               const double (&a0)[WJ], double cg, const double (&c)[WJ],
-                                               const double (&up)[WJ], double (&k)[WJ]) {
-  double S = 0.0;
+// registers for the whole tile).  C cells are solved side by side: their shuffle chains are independent, so
+// interleaving them hides the shuffle / reciprocal latency a single cell would expose.
+// Returns the (warp-uniform) mask of cells where partial pivoting would exchange rows (their k[] is invalid).
+template <int WJ, int C>
+__device__ __forceinline__ unsigned warp_cells_fast(int n, int lane, const double (&K)[WJ], const double (&feNK)[WJ],
+                                                    const double (&a0)[WJ], double cg, const double (&c)[C][WJ],
+                                                    const double (&up)[C][WJ], double (&k)[C][WJ]) {
+  double S[C];
 #pragma unroll
-  for (int j = 0; j < WJ; ++j) S = fma(K[j], c[j], S);  // absent species carry K = 0
-  S = warp_sum(S);
-  const double rD = fast_rcp(1.0 + S);
-  const double rD2 = rD * rD;
-  double p[WJ], alpha[WJ], z[WJ], v[WJ], h[WJ];
-  double run = 0.0, qz = 0.0;
+  for (int q = 0; q < C; ++q) {
+    S[q] = 0.0;
+#pragma unroll
+    for (int j = 0; j < WJ; ++j) S[q] = fma(K[j], c[q][j], S[q]);  // absent species carry K = 0
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int q = 0; q < C; ++q) S[q] += __shfl_xor_sync(kFull, S[q], o);
+  double rD[C], rD2[C], run[C], qz[C];
+#pragma unroll
+  for (int q = 0; q < C; ++q) {
+    rD[q] = fast_rcp(1.0 + S[q]);
+    rD2[q] = rD[q] * rD[q];
+    run[q] = 0.0;
+    qz[q] = 0.0;
+  }
+  double p[C][WJ], alpha[C][WJ], z[C][WJ], v[C][WJ], h[C][WJ];
 #pragma unroll
   for (int j = 0; j < WJ; ++j) {
-    p[j] = feNK[j] * c[j] * rD2;              // fe nbar K c / D^2
-    alpha[j] = fma(feNK[j], rD, a0[j]);       // 1 + fe (lambda + nbar K / D)
-    const double ra = fast_rcp(alpha[j]);
-    z[j] = (c[j] - up[j]) * cg * ra;
-    v[j] = p[j] * ra;
-    const double t = K[j] * v[j];             // p_i q_i / alpha_i
-    qz = fma(K[j], z[j], qz);
-    double incl = t;                          // inclusive scan over the 32 species of block j
+    double incl[C];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double u = __shfl_up_sync(kFull, incl, o);
-      if (lane >= o) incl += u;
+    for (int q = 0; q < C; ++q) {
+      p[q][j] = feNK[j] * c[q][j] * rD2[q];          // fe nbar K c / D^2
+      alpha[q][j] = fma(feNK[j], rD[q], a0[j]);      // 1 + fe (lambda + nbar K / D)
+      const double ra = fast_rcp(alpha[q][j]);
+      z[q][j] = (c[q][j] - up[q][j]) * cg * ra;
+      v[q][j] = p[q][j] * ra;
+      incl[q] = K[j] * v[q][j];                      // p_i q_i / alpha_i
+      qz[q] = fma(K[j], z[q][j], qz[q]);
     }
-    double excl = __shfl_up_sync(kFull, incl, 1);
-    if (lane == 0) excl = 0.0;
-    h[j] = 1.0 - (run + excl);                // h_i = 1 - sum_{r<i} p_r q_r / alpha_r
-    run += __shfl_sync(kFull, incl, 31);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)                 // inclusive scan over the 32 species of block j
+#pragma unroll
+      for (int q = 0; q < C; ++q) {
+        const double u = __shfl_up_sync(kFull, incl[q], o);
+        if (lane >= o) incl[q] += u;
+      }
+#pragma unroll
+    for (int q = 0; q < C; ++q) {
+      double excl = __shfl_up_sync(kFull, incl[q], 1);
+      if (lane == 0) excl = 0.0;
+      h[q][j] = 1.0 - (run[q] + excl);               // h_i = 1 - sum_{r<i} p_r q_r / alpha_r
+      run[q] += __shfl_sync(kFull, incl[q], 31);
+    }
   }
   // partial-pivoting test: q_i * max_{r>i} |p_r|  >  |alpha_i h_i - p_i q_i|   (h_i > 0)
-  bool redo = false;
-  double runmax = 0.0;
+  unsigned redo = 0u;
+  double runmax[C];
+#pragma unroll
+  for (int q = 0; q < C; ++q) runmax[q] = 0.0;
 #pragma unroll
   for (int j = WJ - 1; j >= 0; --j) {
-    double sfx = fabs(p[j]);  // inclusive suffix maximum inside block j
+    double sfx[C];  // inclusive suffix maximum inside block j
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double u = __shfl_down_sync(kFull, sfx, o);
-      if (lane + o < 32) sfx = fmax(sfx, u);
-    }
-    double excl = __shfl_down_sync(kFull, sfx, 1);
-    if (lane == 31) excl = 0.0;
-    const double below = fmax(runmax, excl);
-    runmax = fmax(runmax, __shfl_sync(kFull, sfx, 0));
-    if (lane + 32 * j < n) {
-      const double dpiv = fabs(fma(alpha[j], h[j], -(p[j] * K[j])));
-      redo |= !(h[j] > 0.0) || (K[j] * below > dpiv) || (dpiv == 0.0);
+    for (int q = 0; q < C; ++q) sfx[q] = fabs(p[q][j]);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+#pragma unroll
+      for (int q = 0; q < C; ++q) {
+        const double u = __shfl_down_sync(kFull, sfx[q], o);
+        if (lane + o < 32) sfx[q] = fmax(sfx[q], u);
+      }
+#pragma unroll
+    for (int q = 0; q < C; ++q) {
+      double excl = __shfl_down_sync(kFull, sfx[q], 1);
+      if (lane == 31) excl = 0.0;
+      const double below = fmax(runmax[q], excl);
+      runmax[q] = fmax(runmax[q], __shfl_sync(kFull, sfx[q], 0));
+      if (lane + 32 * j < n) {
+        const double dpiv = fabs(fma(alpha[q][j], h[q][j], -(p[q][j] * K[j])));
+        if (!(h[q][j] > 0.0) || (K[j] * below > dpiv) || (dpiv == 0.0)) redo |= 1u << q;
+      }
     }
   }
-  qz = warp_sum(qz);
-  const double f = qz * fast_rcp(1.0 - run);  // (q.z) / (1 - q.v)
 #pragma unroll
-  for (int j = 0; j < WJ; ++j) k[j] = fma(v[j], f, z[j]);
-  return __any_sync(kFull, redo);
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int q = 0; q < C; ++q) qz[q] += __shfl_xor_sync(kFull, qz[q], o);
+#pragma unroll
+  for (int q = 0; q < C; ++q) {
+    const double f = qz[q] * fast_rcp(1.0 - run[q]);  // (q.z) / (1 - q.v)
+#pragma unroll
+    for (int j = 0; j < WJ; ++j) k[q][j] = fma(v[q][j], f, z[q][j]);
+  }
+  return __reduce_or_sync(kFull, redo);
 }
 
 // ---- warp per cell, EXACT: compute_row with nalgebra's LU inverse and gemv -----------------------------
@@ -326,8 +363,11 @@ __device__ __noinline__ void warp_cell_exact(int n, int lane, const SpeciesConst
 }
 
 // ---- kernel -----------------------------------------------------------------------------------------------
+// threads per CTA of the warp-per-cell variants: 16 warps where the lane state is small (FAST, <= 2 species per lane)
+constexpr int tiled_warp_threads(int WJ, int ARITH) { return (ARITH != CHROM_ARITH_EXACT && WJ <= 2) ? 512 : 256; }
+
 template <int N, int METHOD, int ARITH, int WJ>
-__global__ void __launch_bounds__(WJ > 0 ? 256 : multi_max_threads(N, ARITH), 1)
+__global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi_max_threads(N, ARITH), 1)
     k_multi_tiled(const BatchDev b, double* scratch, const TiledArgs a) {
   constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
   constexpr bool EXACT = (ARITH == CHROM_ARITH_EXACT);
@@ -426,33 +466,54 @@ __global__ void __launch_bounds__(WJ > 0 ? 256 : multi_max_threads(N, ARITH), 1)
       StageCtx st{Y, ACC, DST, pitch, METHOD == CHROM_EULER ? 0 : stage, dt, h2, h6};
       const double* inlet_row = inlet + irow * n;
       if constexpr (WJ > 0) {
-        for (uint32_t cc = (uint32_t)warp; cc < ncell; cc += (uint32_t)W) {
-          double k[WJC];
-          if constexpr (EXACT) {
+        if constexpr (EXACT) {
+          for (uint32_t cc = (uint32_t)warp; cc < ncell; cc += (uint32_t)W) {
+            double k[WJC];
             warp_cell_exact<WJC>(n, lane, sc, fe, ue, dz, SRC, inlet_row, pitch, cc, warp_scratch, k);
-          } else {
-            double c[WJC], up[WJC];
+            bool cell_bad = false;
 #pragma unroll
             for (int j = 0; j < WJC; ++j) {
               const int s = lane + 32 * j;
-              c[j] = (s < n) ? SRC[(size_t)s * pitch + cc] : 0.0;
-              up[j] = (s < n) ? ((cc > 0) ? SRC[(size_t)s * pitch + cc - 1] : inlet_row[s]) : 0.0;
+              if (s < n) cell_bad |= stage_one<true>(st, (size_t)s * pitch + cc, k[j]);
             }
-            if (warp_cell_fast<WJC>(n, lane, wK, wF, wA, cg, c, up, k)) {
-              warp_dense_fast(n, sc, cg, SRC, inlet_row, pitch, cc, warp_scratch, lane);
-              const double* vec = warp_scratch + (size_t)n * n;
+            bad |= cell_bad && (cc >= first_valid);
+          }
+        } else {
+          constexpr int C = WJC == 1 ? 4 : (WJC == 2 ? 2 : 1);  // cells solved side by side per warp
+          for (uint32_t cc0 = (uint32_t)(warp * C); cc0 < ncell; cc0 += (uint32_t)(W * C)) {
+            double c[C][WJC], up[C][WJC], k[C][WJC];
 #pragma unroll
-              for (int j = 0; j < WJC; ++j) k[j] = (lane + 32 * j < n) ? vec[lane + 32 * j] : 0.0;
-              __syncwarp();
+            for (int q = 0; q < C; ++q) {
+              const uint32_t cc = min(cc0 + (uint32_t)q, ncell - 1u);  // past the tile: recomputed, never stored
+#pragma unroll
+              for (int j = 0; j < WJC; ++j) {
+                const int s = lane + 32 * j;
+                c[q][j] = (s < n) ? SRC[(size_t)s * pitch + cc] : 0.0;
+                up[q][j] = (s < n) ? ((cc > 0) ? SRC[(size_t)s * pitch + cc - 1] : inlet_row[s]) : 0.0;
+              }
+            }
+            const unsigned redo = warp_cells_fast<WJC, C>(n, lane, wK, wF, wA, cg, c, up, k);
+#pragma unroll
+            for (int q = 0; q < C; ++q) {
+              const uint32_t cc = cc0 + (uint32_t)q;
+              if (cc < ncell) {
+                if ((redo >> q) & 1u) {  // warp-uniform: redo this cell with the dense row-exchanging LU
+                  warp_dense_fast(n, sc, cg, SRC, inlet_row, pitch, cc, warp_scratch, lane);
+                  const double* vec = warp_scratch + (size_t)n * n;
+#pragma unroll
+                  for (int j = 0; j < WJC; ++j) k[q][j] = (lane + 32 * j < n) ? vec[lane + 32 * j] : 0.0;
+                  __syncwarp();
+                }
+                bool cell_bad = false;
+#pragma unroll
+                for (int j = 0; j < WJC; ++j) {
+                  const int s = lane + 32 * j;
+                  if (s < n) cell_bad |= stage_one<false>(st, (size_t)s * pitch + cc, k[q][j]);
+                }
+                bad |= cell_bad && (cc >= first_valid);
+              }
             }
           }
-          bool cell_bad = false;
-#pragma unroll
-          for (int j = 0; j < WJC; ++j) {
-            const int s = lane + 32 * j;
-            if (s < n) cell_bad |= stage_one<EXACT>(st, (size_t)s * pitch + cc, k[j]);
-          }
-          bad |= cell_bad && (cc >= first_valid);
         }
       } else {
         const int cpt = (int)((a.tw + T - 1) / T);
