@@ -317,6 +317,7 @@ def main():
                     help="multi-species workloads: dense register LU (fast) or structured LU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     args = ap.parse_args()
 
     spec = workload_spec(args.workload)
@@ -340,6 +341,10 @@ def main():
     from chromatography_b200 import _ffi
     lib = _ffi.lib()
     ctx = cb.Context([local_rank])
+    # multi-GPU hosts: keep this rank's thread and its page-locked buffers on the NUMA node of its GPU
+    # (restored before the CPU baseline, which uses every host core)
+    affinity0 = os.sched_getaffinity(0)
+    numa = ctx.bind_host_thread(0) if not args.no_numa else (-1, 0)
 
     n_cols = args.cols or spec["n_cols"]
     inp = build_inputs(spec, n_cols, rank)
@@ -415,7 +420,8 @@ def main():
         e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
         e2e = {"value": sum_over_ranks(units_rank) * e_steps / (e_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e_ms / e_steps,
-               "steps": e_steps, "api": "chrom_cuda_solve_%s_batch, pinned host buffers" % spec["kind"]}
+               "steps": e_steps, "api": "chrom_cuda_solve_%s_batch, pinned host buffers" % spec["kind"],
+               "host_numa_node": numa[0], "host_cpus_bound": numa[1]}
         # The same call in the sweep mode the ABI offers: per-column on-device summaries
         # (area, first moment, max, time of max) + final state + status instead of the full-rate outlet
         # series.  Reported beside e2e, never instead of it: the D2H volume is what differs.
@@ -447,6 +453,7 @@ def main():
 
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------------
     cpu = None
+    os.sched_setaffinity(0, affinity0)
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = host_cores()
         n, csteps = cpu_sample_size(spec, cores)

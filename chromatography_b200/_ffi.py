@@ -60,6 +60,7 @@ SYMBOLS = {
     "chrom_cuda_last_timing": (C.c_int32, [_vp, C.POINTER(Timing)]),
     "chrom_cuda_host_alloc": (C.c_int32, [C.c_size_t, C.POINTER(_vp)]),
     "chrom_cuda_host_free": (None, [_vp]),
+    "chrom_cuda_bind_host_thread": (C.c_int32, [_vp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "chrom_cuda_validate_cfg": (C.c_char_p, [C.POINTER(RunCfg)]),
     "chrom_cuda_n_samples": (C.c_uint64, [C.c_uint64, C.c_uint64]),
     "chrom_cuda_time_points": (None, [C.c_double, C.c_uint64, _dp]),

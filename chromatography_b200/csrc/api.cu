@@ -15,6 +15,10 @@
 #include <string>
 #include <vector>
 
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include "kernels.h"
 
 using namespace chrom;
@@ -496,6 +500,51 @@ int32_t chrom_cuda_host_alloc(size_t bytes, void** out) {
 
 void chrom_cuda_host_free(void* p) {
   if (p) cudaFreeHost(p);
+}
+
+int32_t chrom_cuda_bind_host_thread(chrom_cuda_ctx* ctx, int32_t device_index, int32_t* numa_node, int32_t* n_cpus) {
+  if (numa_node) *numa_node = -1;
+  if (n_cpus) *n_cpus = 0;
+  if (!ctx || device_index < 0 || device_index >= (int)ctx->devs.size()) return CHROM_ERR_INVALID;
+  char bus[32] = {0};
+  CUDA_TRY(ctx, cudaDeviceGetPCIBusId(bus, sizeof bus, ctx->devs[device_index].id));
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  int node = -1;
+  if (FILE* f = fopen(format("/sys/bus/pci/devices/%s/numa_node", bus).c_str(), "r")) {
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+  }
+  if (node < 0) return CHROM_OK;  // single-node host or no topology information: leave the thread alone
+  cpu_set_t allowed, want;
+  CPU_ZERO(&want);
+  if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return CHROM_OK;
+  if (FILE* f = fopen(format("/sys/devices/system/node/node%d/cpulist", node).c_str(), "r")) {
+    int a = 0, b = 0;
+    for (;;) {  // "0-15,32-47"
+      if (fscanf(f, "%d", &a) != 1) break;
+      b = a;
+      int ch = fgetc(f);
+      if (ch == '-') {
+        if (fscanf(f, "%d", &b) != 1) break;
+        ch = fgetc(f);
+      }
+      for (int c = a; c <= b && c < CPU_SETSIZE; ++c)
+        if (CPU_ISSET(c, &allowed)) CPU_SET(c, &want);
+      if (ch != ',') break;
+    }
+    fclose(f);
+  }
+  const int count = CPU_COUNT(&want);
+  if (count == 0) return CHROM_OK;  // the process is confined to another node: nothing sensible to do
+  if (sched_setaffinity(0, sizeof want, &want) != 0) return CHROM_OK;
+  if (node < 1024) {  // prefer the node for this thread's allocations (MPOL_PREFERRED = 1); best effort
+    unsigned long mask[1024 / (8 * sizeof(unsigned long))] = {0};
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    (void)syscall(SYS_set_mempolicy, 1, mask, 1024ul + 1);
+  }
+  if (numa_node) *numa_node = node;
+  if (n_cpus) *n_cpus = count;
+  return CHROM_OK;
 }
 
 // ---- host helpers ---------------------------------------------------------------------------

@@ -164,6 +164,13 @@ class Context:
         self._lib.chrom_cuda_last_timing(self._h, C.byref(t))
         return {n: getattr(t, n) for n, _ in _ffi.Timing._fields_}
 
+    def bind_host_thread(self, device_index=0) -> tuple:
+        """Pin the calling thread (and its later allocations) to the NUMA node of the device: (node, n_cpus);
+        node == -1 when the host exposes no topology (nothing changed)."""
+        node, ncpu = C.c_int32(-1), C.c_int32(0)
+        self.check(self._lib.chrom_cuda_bind_host_thread(self._h, device_index, C.byref(node), C.byref(ncpu)))
+        return node.value, ncpu.value
+
     def flush_l2(self) -> None:
         self.check(self._lib.chrom_cuda_flush_l2(self._h))
 

@@ -116,6 +116,14 @@ int32_t chrom_cuda_last_timing(const chrom_cuda_ctx* ctx, chrom_cuda_timing* out
 int32_t chrom_cuda_host_alloc(size_t bytes, void** out);
 void chrom_cuda_host_free(void* p);
 
+/* Multi-GPU hosts: pins the CALLING thread to the CPUs of the NUMA node device `device_index` of the context
+ * hangs off (sysfs: the device's PCI numa_node and that node's cpulist, intersected with the CPUs the process may
+ * use) and prefers that node for the thread's allocations, so that page-locked buffers allocated afterwards and
+ * the copy-back of outlet series do not cross the socket interconnect.  Call it before chrom_cuda_host_alloc.
+ * *numa_node = the node (-1: unknown, nothing changed), *n_cpus = CPUs in the new affinity mask.  Either may be NULL.
+ * No reference counterpart (the reference is a single-process CPU library). */
+int32_t chrom_cuda_bind_host_thread(chrom_cuda_ctx* ctx, int32_t device_index, int32_t* numa_node, int32_t* n_cpus);
+
 /* ---- host-side helpers (pure CPU, no device needed) ------------------------------------------ */
 /* Error text of SolverType::validate; NULL when the configuration is valid. */
 const char* chrom_cuda_validate_cfg(const chrom_run_cfg* cfg);
