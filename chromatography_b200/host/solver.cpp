@@ -7,7 +7,11 @@
 #include "chrom/solver.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <cstdio>
+#include <map>
+#include <thread>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -351,9 +355,86 @@ Result<SimulationResult> CudaSolverBase::solve(const Scenario& scenario, const S
   return std::move(r.unwrap()[0]);
 }
 
+Result<std::vector<Result<SimulationResult>>> CudaSolverBase::solve_scan(const std::vector<const Scenario*>& scenarios,
+                                                                         const std::vector<SolverConfiguration>& configs,
+                                                                         const BatchOptions& opt,
+                                                                         std::size_t max_concurrent) const {
+  if (configs.size() != scenarios.size()) return Err("solve_scan needs one SolverConfiguration per scenario");
+  // group key: model type / grid / species count / time grid.  Anything solve_batch would reject per
+  // scenario (unsupported model, bad initial condition) still reaches it and gets its own error entry.
+  struct Group {
+    std::vector<std::size_t> idx;
+  };
+  std::vector<Group> groups;
+  std::map<std::string, std::size_t> by_key;
+  for (std::size_t i = 0; i < scenarios.size(); ++i) {
+    const Scenario& sc = *scenarios[i];
+    const SolverType& st = configs[i].solver_type;
+    const auto* m = dynamic_cast<const LangmuirMulti*>(sc.model.get());
+    char key[160];
+    std::uint64_t tbits;
+    std::memcpy(&tbits, &st.total_time, 8);
+    snprintf(key, sizeof key, "%s|%zu|%zu|%d|%llx|%llu", sc.model->name(), (std::size_t)sc.model->points(),
+             m ? (std::size_t)m->n_species() : (std::size_t)1, (int)st.kind(), (unsigned long long)tbits,
+             (unsigned long long)st.time_steps);
+    auto it = by_key.find(key);
+    if (it == by_key.end()) {
+      it = by_key.emplace(key, groups.size()).first;
+      groups.emplace_back();
+    }
+    groups[it->second].idx.push_back(i);
+  }
+  std::vector<Result<SimulationResult>> results;
+  results.reserve(scenarios.size());
+  for (std::size_t i = 0; i < scenarios.size(); ++i) results.emplace_back(Err(std::string("not solved")));
+  const std::size_t workers = std::max<std::size_t>(1, std::min(max_concurrent, groups.size()));
+  std::atomic<std::size_t> next{0};
+  std::mutex err_mu;
+  std::string fatal;
+  auto work = [&](std::size_t w) {
+    // worker 0 keeps this solver's context; the others get their own (one context = one set of streams)
+    std::shared_ptr<CudaContext> ctx = (w == 0) ? ctx_ : nullptr;
+    for (;;) {
+      const std::size_t g = next.fetch_add(1);
+      if (g >= groups.size()) return;
+      if (!ctx) {
+        auto c = (w == 0) ? CudaContext::global() : CudaContext::create();
+        if (c.is_err()) {
+          std::lock_guard<std::mutex> lk(err_mu);
+          fatal = c.unwrap_err();
+          return;
+        }
+        ctx = c.unwrap();
+      }
+      std::vector<const Scenario*> sub;
+      for (std::size_t i : groups[g].idx) sub.push_back(scenarios[i]);
+      auto r = solve_batch_on(ctx, sub, configs[groups[g].idx[0]], opt);
+      if (r.is_err()) {  // a failure of the whole group (invalid configuration, ...): every member reports it
+        for (std::size_t i : groups[g].idx) results[i] = Err(r.unwrap_err());
+        continue;
+      }
+      auto v = std::move(r.unwrap());
+      for (std::size_t k = 0; k < v.size(); ++k) results[groups[g].idx[k]] = std::move(v[k]);
+    }
+  };
+  std::vector<std::thread> threads;
+  for (std::size_t w = 1; w < workers; ++w) threads.emplace_back(work, w);
+  work(0);
+  for (auto& t : threads) t.join();
+  if (!fatal.empty()) return Err(fatal);
+  return results;
+}
+
 Result<std::vector<Result<SimulationResult>>> CudaSolverBase::solve_batch(const std::vector<const Scenario*>& scenarios,
                                                                           const SolverConfiguration& config,
                                                                           const BatchOptions& opt) const {
+  return solve_batch_on(nullptr, scenarios, config, opt);
+}
+
+Result<std::vector<Result<SimulationResult>>> CudaSolverBase::solve_batch_on(std::shared_ptr<CudaContext> on,
+                                                                             const std::vector<const Scenario*>& scenarios,
+                                                                             const SolverConfiguration& config,
+                                                                             const BatchOptions& opt) const {
   // ====== Step 1: validation (rk4.rs:213-231) ======
   {
     auto v = config.validate();
@@ -498,7 +579,7 @@ Result<std::vector<Result<SimulationResult>>> CudaSolverBase::solve_batch(const 
   const bool zero_ic = !any_nonzero_bits(y0.data(), y0.size());  // setup_initial_state: skip the upload
 
   // the context first: without a usable GPU this is where the call fails (there is no CPU path)
-  std::shared_ptr<CudaContext> ctx = ctx_;
+  std::shared_ptr<CudaContext> ctx = on ? on : ctx_;
   if (!ctx) {
     auto g = CudaContext::global();
     if (g.is_err()) return Err(g.unwrap_err());

@@ -473,6 +473,49 @@ class _CudaSolver:
         return results
 
 
+    def solve_scan(self, scenarios, configs, max_concurrent=4, **batch_options) -> list:
+        """Heterogeneous sweeps (a different time grid / spatial grid / model type per scenario: the reference's
+        sequential loops in examples/cfl_stability_scan.rs:378-394, stiffness_convergence.rs:360,
+        spatial_temporal_convergence.rs:261-277).  Entries are grouped by (model type, n_points, species count,
+        configuration); each group is one device batch and up to `max_concurrent` groups run at the same time,
+        each on its own context and host thread (distinct contexts are thread-safe).  Entry i is what
+        solve(scenarios[i], configs[i]) would have returned, or its SolverError."""
+        from concurrent.futures import ThreadPoolExecutor
+        import threading
+        if len(configs) != len(scenarios):
+            raise SolverError("solve_scan needs one SolverConfiguration per scenario")
+        groups: dict = {}
+        for i, (sc, cf) in enumerate(zip(scenarios, configs)):
+            m, st = sc.model, cf.solver_type
+            key = (type(m).__name__, m.points(), m.n_species() if isinstance(m, LangmuirMulti) else 1, st.kind,
+                   getattr(st, "total_time", None), getattr(st, "time_steps", None))
+            groups.setdefault(key, []).append(i)
+        results: list = [None] * len(scenarios)
+        local = threading.local()
+        first_ctx = self.ctx
+
+        def run(idx):
+            if getattr(local, "solver", None) is None:
+                with lock:
+                    own = first_ctx if not taken else Context()
+                    taken.append(own)
+                local.solver = type(self)(own, self.arith, self.full_trajectory)
+            try:
+                out = local.solver.solve_batch([scenarios[i] for i in idx], configs[idx[0]], **batch_options)
+            except SolverError as e:      # a failure of the whole group: every member reports it
+                out = [e] * len(idx)
+            for i, r in zip(idx, out):
+                results[i] = r
+
+        lock, taken = threading.Lock(), []
+        with ThreadPoolExecutor(max_workers=max(1, min(max_concurrent, len(groups)))) as pool:
+            list(pool.map(run, groups.values()))
+        for c in taken:
+            if c is not first_ctx:
+                c.close()
+        return results
+
+
 class CudaRK4Solver(_CudaSolver):
     METHOD = _ffi.RK4
     NAME = "Runge Kutta (RK4)"        # rk4.rs:352-354

@@ -216,6 +216,17 @@ class CudaSolverBase : public Solver {
   Result<std::vector<Result<SimulationResult>>> solve_batch(const std::vector<const Scenario*>& scenarios,
                                                             const SolverConfiguration& config,
                                                             const BatchOptions& options = BatchOptions()) const;
+  // Heterogeneous sweeps — a different time grid (CFL / stiffness scans: examples/cfl_stability_scan.rs:378-394,
+  // stiffness_convergence.rs:360), spatial grid (spatial_temporal_convergence.rs:261-277) or model type per
+  // scenario.  Entries are grouped by (model type, n_points, species count, configuration); every group is ONE
+  // device batch, and up to `max_concurrent` groups run at the same time, each on its own libchrom_cuda context
+  // and host thread (distinct contexts are thread-safe), so that small groups share the GPU instead of
+  // queueing.  configs.size() must equal scenarios.size().  Entry i is what solve(scenarios[i], configs[i])
+  // would have returned.
+  Result<std::vector<Result<SimulationResult>>> solve_scan(const std::vector<const Scenario*>& scenarios,
+                                                           const std::vector<SolverConfiguration>& configs,
+                                                           const BatchOptions& options = BatchOptions(),
+                                                           std::size_t max_concurrent = 4) const;
   void set_arithmetic(Arithmetic a) { arith_ = a; }
   Arithmetic arithmetic() const { return arith_; }
   void set_context(std::shared_ptr<CudaContext> ctx) { ctx_ = std::move(ctx); }
@@ -226,6 +237,11 @@ class CudaSolverBase : public Solver {
   CudaSolverBase(int method, const char* meta_solver) : method_(method), meta_solver_(meta_solver) {}
 
  private:
+  // solve_batch on an explicit context (solve_scan's workers); nullptr = this solver's / the global context
+  Result<std::vector<Result<SimulationResult>>> solve_batch_on(std::shared_ptr<CudaContext> on,
+                                                               const std::vector<const Scenario*>& scenarios,
+                                                               const SolverConfiguration& config,
+                                                               const BatchOptions& options) const;
   int method_;
   const char* meta_solver_;
   Arithmetic arith_ = Arithmetic::Fast;

@@ -272,4 +272,54 @@ TEST(test_strided_trajectory) {
   }
 }
 
+TEST(test_solve_scan_equals_individual_solves) {
+  // examples/cfl_stability_scan.rs:378-394 runs one solve per CFL target (a different step count each) in a
+  // sequential loop; spatial_temporal_convergence.rs:261-277 also varies the grid.  solve_scan runs the groups
+  // concurrently; every entry must equal its own solve(), bit for bit, whatever group / context it ran on.
+  std::vector<Scenario> scs;
+  std::vector<SolverConfiguration> cfgs;
+  for (std::size_t steps : {400u, 800u, 1200u, 2000u, 800u, 400u}) {
+    scs.push_back(tfa_scenario(TemporalInjection::gaussian(10.0, 3.0, 0.1), 0.2 + 1e-4 * (double)steps));
+    cfgs.push_back(SolverConfiguration::time_evolution(120.0, steps));
+  }
+  {  // another grid (nz = 60) and a two-species model in the same scan
+    auto fine = std::make_unique<LangmuirSingle>(1.2, 0.4, 2.0, 0.4, 0.001, 0.25, 60, TemporalInjection::gaussian(10.0, 3.0, 0.1));
+    auto init = fine->setup_initial_state();
+    scs.push_back(Scenario(std::move(fine), DomainBoundaries::temporal(std::move(init))));
+    cfgs.push_back(SolverConfiguration::time_evolution(120.0, 800));
+    std::vector<SpeciesParams> sp;
+    sp.emplace_back("Ascorbic", 1.0, 1.1, 2, TemporalInjection::gaussian(10.0, 3.0, 0.1));
+    sp.emplace_back("Erythorbic", 1.0, 1.7, 2, TemporalInjection::gaussian(10.0, 3.0, 0.1));
+    auto multi = std::make_unique<LangmuirMulti>(LangmuirMulti::create(std::move(sp), 100, 0.4, 0.001, 0.25).unwrap());
+    auto minit = multi->setup_initial_state();
+    scs.push_back(Scenario(std::move(multi), DomainBoundaries::temporal(std::move(minit))));
+    cfgs.push_back(SolverConfiguration::time_evolution(120.0, 800));
+  }
+  scs.push_back(Scenario(std::make_unique<LangmuirSingle>(1.2, 0.4, 2.0, 0.4, 0.001, 0.25, 100, TemporalInjection::none()),
+                         DomainBoundaries()));  // invalid: its own Err
+  cfgs.push_back(SolverConfiguration::time_evolution(120.0, 400));
+  std::vector<const Scenario*> ptrs;
+  for (auto& s : scs) ptrs.push_back(&s);
+  RK4Solver solver;
+  BatchOptions opt;
+  opt.snapshot_stride = 0;
+  auto scan = solver.solve_scan(ptrs, cfgs, opt, 3).unwrap();
+  CHECK_EQ(scan.size(), scs.size());
+  CHECK_STR_EQ(scan.back().unwrap_err(), "Dimension boundaries cannot be empty.");
+  for (std::size_t i = 0; i + 1 < scs.size(); ++i) {
+    auto one = solver.solve(scs[i], cfgs[i]).unwrap();
+    const auto& b = scan[i].unwrap();
+    CHECK_EQ(b.len(), one.len());
+    CHECK(b.time_points == one.time_points);
+    CHECK(b.outlet == one.outlet);
+    const PhysicalData* fa = b.final_state.get(PhysicalQuantity::Concentration);
+    const PhysicalData* fb = one.final_state.get(PhysicalQuantity::Concentration);
+    if (fa->is_vector()) CHECK(fa->as_vector() == fb->as_vector());
+    else CHECK(fa->as_matrix().data == fb->as_matrix().data);
+  }
+  // mismatched argument lengths are an error of the whole call
+  cfgs.pop_back();
+  CHECK(solver.solve_scan(ptrs, cfgs, opt).is_err());
+}
+
 int main(int argc, char** argv) { return minitest::run(argc, argv); }

@@ -256,3 +256,38 @@ def test_pipelined_one_shot_equals_plan_and_oracle(ctx):
     oo, of, _ = O.solve_single_batch([to_oracle(models[i]) for i in pick], O.RK4, T, steps)
     assert_bit_equal(one.outlet[pick], oo, "outlet vs oracle")
     assert_bit_equal(one.final_state[pick], of, "final vs oracle")
+
+
+def test_solve_scan_cfl_sweep(ctx):
+    """The reference's CFL scan (examples/cfl_stability_scan.rs:378-394: one solve per step count, sequential loop)
+    and spatial-convergence scan (spatial_temporal_convergence.rs:261-277: one per grid) as ONE solve_scan call:
+    groups run concurrently on their own contexts; every entry equals its own oracle solve bit for bit, unstable
+    entries carry the reference's validate_state error."""
+    T = 6000.0
+    scenarios, configs, expect = [], [], []
+    for steps in (100, 1500, 4000, 10000, 1500, 4000):  # CFL from unstable (NaN at step 62) to comfortable, two repeated
+        m = W.tfa_single()
+        scenarios.append(cb.Scenario.new(m, cb.DomainBoundaries.temporal(m.setup_initial_state())))
+        configs.append(cb.SolverConfiguration.time_evolution(T, steps))
+        expect.append((m, steps))
+    for nz in (50, 200):
+        m = W.tfa_single(nz=nz)
+        scenarios.append(cb.Scenario.new(m, cb.DomainBoundaries.temporal(m.setup_initial_state())))
+        configs.append(cb.SolverConfiguration.time_evolution(T, 20000))
+        expect.append((m, 20000))
+    solver = cb.CudaRK4Solver(ctx, arith=cb.ARITH_EXACT, full_trajectory=False)
+    out = solver.solve_scan(scenarios, configs, max_concurrent=3)
+    assert len(out) == len(scenarios)
+    n_err = 0
+    for r, (m, steps) in zip(out, expect):
+        ref = O.solve_single(to_oracle(m), O.RK4, T, steps)
+        if ref.status != 0:
+            n_err += 1
+            assert isinstance(r, cb.SolverError) and str(r) == cb.status_message(ref.status)
+            continue
+        assert_bit_equal(r.final_state, ref.final_state, f"steps={steps} nz={m.points()} final")
+        assert_bit_equal(r.outlet, ref.outlet, f"steps={steps} nz={m.points()} outlet")
+        assert r.metadata["time steps"] == str(steps)
+    assert 0 < n_err < len(out)  # the scan crosses the stability limit
+    with pytest.raises(cb.SolverError, match="one SolverConfiguration per scenario"):
+        solver.solve_scan(scenarios, configs[:-1])
