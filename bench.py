@@ -313,8 +313,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--cols", type=int, default=0, help="override columns per GPU (debug only; invalidates the metric)")
-    ap.add_argument("--arith", default="fast", choices=["fast", "structured"],
-                    help="multi-species workloads: dense register LU (fast) or structured LU")
+    ap.add_argument("--arith", default="fast", choices=["fast", "dense"],
+                    help="multi-species workloads: closed-form structured LU (fast, the library default) or the "
+                         "dense register LU with partial pivoting (dense)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
@@ -350,11 +351,14 @@ def main():
     inp = build_inputs(spec, n_cols, rank)
     n_cols = len(inp["cols"])
     units_rank = units_of(spec, n_cols)
-    arith = cb.ARITH_FAST_STRUCTURED if (args.arith == "structured" and spec["kind"] == "multi") else cb.ARITH_FAST
-    if arith == cb.ARITH_FAST_STRUCTURED:
-        # structured LU: ~28 flops per species per cell-stage (4 setup, 2 pivot bound, 15 forward incl. one
-        # reciprocal, 3 back substitution, 3.25 stage algebra) + 8 per cell; the 776 of SURVEY §8d is dense LU
-        spec = dict(spec, flops=28.0 * spec["n_species"] + 8.0)
+    arith = cb.ARITH_FAST
+    if spec["kind"] == "multi":
+        if args.arith == "dense":
+            arith = cb.ARITH_FAST_DENSE  # the dense register LU: SURVEY 8d's 776 flops per cell-stage at n = 8
+        else:
+            # FAST = the closed-form structured elimination: per species b 2, S 2, p 1, alpha 2, 1/alpha 1, z 1, v 2,
+            # q.v 2, q.z 2, x 2, stage algebra 3.25 = 20.25 flops; per cell 1+S, 1/D, 1/D^2, 1-q.v, f 2, pivot bound 4 = 10
+            spec = dict(spec, flops=20.25 * spec["n_species"] + 10.0)
     cfg = cb.make_cfg(cb.RK4, inp["total_time"], spec["steps"], spec["nz"], spec["n_species"], 1, 0, arith)
     want = cb.WANT_OUTLET | cb.WANT_FINAL | cb.WANT_STATUS
 

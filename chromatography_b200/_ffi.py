@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libchrom_cuda.so")
 CHROM_OK = 0
 CHROM_ERR_INVALID, CHROM_ERR_CUDA, CHROM_ERR_UNSUPPORTED, CHROM_ERR_NO_DEVICE = -1, -2, -3, -4
 EULER, RK4 = 0, 1
-ARITH_FAST, ARITH_EXACT, ARITH_FAST_STRUCTURED = 0, 1, 3
+ARITH_FAST, ARITH_EXACT, ARITH_FAST_STRUCTURED, ARITH_FAST_DENSE = 0, 1, 3, 4
 INJ_NONE, INJ_DIRAC, INJ_GAUSSIAN, INJ_RECTANGLE = 0, 1, 2, 3
 WANT_OUTLET, WANT_SNAPSHOTS, WANT_FINAL, WANT_SUMMARY, WANT_STATUS = 1, 2, 4, 8, 16
 

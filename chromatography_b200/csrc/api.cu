@@ -153,7 +153,7 @@ int32_t check_cfg(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, bool multi) {
   if (cfg->method != CHROM_EULER && cfg->method != CHROM_RK4)
     return fail(ctx, CHROM_ERR_INVALID, format("unknown method %d (0 = Euler, 1 = RK4)", cfg->method));
   if (cfg->arith != CHROM_ARITH_FAST && cfg->arith != CHROM_ARITH_EXACT &&
-      !(multi && cfg->arith == CHROM_ARITH_FAST_STRUCTURED))
+      !(multi && (cfg->arith == CHROM_ARITH_FAST_STRUCTURED || cfg->arith == CHROM_ARITH_FAST_DENSE)))
     return fail(ctx, CHROM_ERR_INVALID, format("unknown arith mode %d", cfg->arith));
   if (cfg->n_points < 2)
     return fail(ctx, CHROM_ERR_INVALID, format("Need at least 2 spatial points, got %u", cfg->n_points));
@@ -281,8 +281,14 @@ int32_t build_shard(chrom_cuda_plan* plan, Shard& sh, const chrom_single_col* sc
   } else {
     b.arith = multi_kernel_arith((int)cfg.n_species, cfg.arith);
     const char* force_tiled = getenv("CHROM_MULTI_TILED");  // experiments / tests: tiles even when the column fits
-    ok = !(force_tiled && atoi(force_tiled) != 0) && multi_resident_choose(b, d.sm_count, &sh.g, &why);
+    const bool forced = force_tiled && atoi(force_tiled) != 0;
+    // FAST structured arithmetic, n <= 8, column short enough: everything in registers (multi_reg.cu)
+    const char* no_reg = getenv("CHROM_MULTI_NO_REG");
+    if (!forced && b.arith == CHROM_KARITH_STRUCT && !(no_reg && atoi(no_reg) != 0))
+      ok = multi_reg_choose(b, d.sm_count, &sh.g, &why);
     if (ok) {
+      // no scratch, no streamed state
+    } else if ((ok = !forced && multi_resident_choose(b, d.sm_count, &sh.g, &why))) {
       const size_t per_thread = multi_scratch_per_thread((int)cfg.n_species, b.arith);
       if (per_thread) {
         CUDA_TRY(ctx, sh.scratch.alloc(per_thread * sh.g.grid.x * sh.g.block.x, d.stream));
@@ -401,6 +407,9 @@ int32_t launch_batch(chrom_cuda_ctx* ctx, const BatchDev& b, const LaunchGeom& g
       break;
     case 5:
       e = multi_tiled_launch(b, g, s);
+      break;
+    case 6:
+      e = multi_reg_launch(b, g, s);
       break;
     default:
       return fail(ctx, CHROM_ERR_UNSUPPORTED, "plan has no kernel");

@@ -56,7 +56,8 @@ struct TiledArgs {
 
 // How a kernel family maps a batch onto the machine; filled by the *_choose functions.
 struct LaunchGeom {
-  int kind = 0;           // 1 single_resident, 2 single_resident_mw, 3 single_stream, 4 multi_resident, 5 multi_tiled
+  int kind = 0;           // 1 single_resident, 2 single_resident_mw, 3 single_stream, 4 multi_resident, 5 multi_tiled,
+                          // 6 multi_reg (register-resident multi-species)
   int M = 0;              // cells per lane
   int L = 0;              // lanes per column (resident) / threads per column
   int cpw = 0;            // columns per warp (resident, single warp)
@@ -85,6 +86,10 @@ bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::
 cudaError_t multi_resident_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s);
 int multi_kernel_arith(int n_species, int arith);
 size_t multi_scratch_per_thread(int n_species, int kernel_arith);
+
+// multi_reg.cu — LangmuirMulti n <= 8 with the state in registers (FAST arithmetic)
+bool multi_reg_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why);
+cudaError_t multi_reg_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s);
 
 // multi_tiled.cu — LangmuirMulti beyond the resident capacity (long columns, n > 64): tiles through HBM/L2
 bool multi_tiled_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why);

@@ -1,5 +1,6 @@
 // multi_inst.cu — one translation unit per species count (compiled with -DCHROM_MULTI_N=0..8, 0 = runtime n)
 // so that the nine instantiation sets of multi_kernels.cuh / multi_tiled.cuh build in parallel.
+#include "multi_reg.cuh"
 #include "multi_tiled.cuh"
 
 #define CHROM_CAT2(a, b) a##b
@@ -12,6 +13,14 @@ mkern_t CHROM_CAT(multi_pick_, CHROM_MULTI_N)(int method, int arith) { return pi
 tkern_t CHROM_CAT(multi_tiled_pick_, CHROM_MULTI_N)(int method, int arith, int wj) {
   return pick_tiled_n<CHROM_MULTI_N>(method, arith, wj);
 }
+#if CHROM_MULTI_N > 0
+typedef void (*rkern_t)(const BatchDev);
+rkern_t CHROM_CAT(multi_reg_pick_, CHROM_MULTI_N)(int method, int m) { return pick_reg_n<CHROM_MULTI_N>(method, m); }
+int CHROM_CAT(multi_reg_tmax_, CHROM_MULTI_N)(int m) {  // threads per CTA; negative: acc lives in shared memory
+  const int t = reg_max_threads_rt<CHROM_MULTI_N>(m);
+  return reg_acc_shared_rt<CHROM_MULTI_N>(m) ? -t : t;
+}
+#endif
 #if CHROM_MULTI_N == 0
 void multi_tiled_init_launch(const BatchDev& b, double* ping, unsigned long long* code, cudaStream_t s) {
   k_tiled_init<<<296, 256, 0, s>>>(b, ping, code);

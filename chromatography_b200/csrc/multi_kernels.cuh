@@ -465,6 +465,75 @@ __device__ __forceinline__ bool structured_cell(const SpeciesConst* sc, double c
   return redo;
 }
 
+// The same elimination in closed form (compile-time n, registers).  Eliminating species 0..i-1 of
+// diag(alpha) - p q^T leaves the pivot alpha_i - p_i q_i / h_i with h_i = 1 - sum_{j<i} p_j q_j / alpha_j, and
+// the solution is x = z + v (q.z) / (1 - q.v), z = b / alpha, v = p / alpha: the n reciprocals are independent
+// (the sweep above chains n dependent ones) and the work drops to ~18 FP64 instructions per species.
+// Partial pivoting: rows would be exchanged at step i iff q_i max_{r>i}|p_r| > |alpha_i h_i - p_i q_i|.  A cheap
+// sufficient condition rules that out for the whole cell, 2 max_i q_i max_r|p_r| < min_i alpha_i (1 - q.v)
+// (h_i >= h_n = 1 - q.v for p >= 0); only a cell that fails it evaluates the per-step test, and only a cell
+// that fails THAT is redone with the dense row-exchanging LU by the caller (returns true).
+template <int N>
+__device__ __forceinline__ bool scan_cell(const SpeciesConst* sc, double cg, const double* SRC, const double* inlet_row,
+                                          uint32_t nz, uint32_t cc, double (&x)[N]) {
+  double K[N], pw[N], v[N];
+  double S = 0.0, pmax = 0.0, kmax = 0.0;
+  bool nonneg = true;
+#pragma unroll
+  for (int s = 0; s < N; ++s) {
+    const double c = SRC[(size_t)s * nz + cc];
+    const double up = (cc > 0) ? SRC[(size_t)s * nz + cc - 1] : inlet_row[s];
+    const double2 kf = *reinterpret_cast<const double2*>(&sc[s].K);  // {K, feNK}
+    K[s] = kf.x;
+    x[s] = (c - up) * cg;
+    S = fma(kf.x, c, S);
+    pw[s] = kf.y * c;  // feNK_s * c_s; p_s = pw_s / D^2
+    pmax = fmax(pmax, fabs(pw[s]));
+    kmax = fmax(kmax, kf.x);
+    nonneg &= (__double2hiint(pw[s]) >= 0);
+  }
+  const double rD = fast_rcp(1.0 + S);
+  const double rD2 = rD * rD;
+  double qv = 0.0, qz = 0.0, amin = 1e300;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const double2 af = *reinterpret_cast<const double2*>(&sc[i].a0);  // {a0, feNK}
+    const double alpha = fma(af.y, rD, af.x);                        // 1 + fe*(lambda_i + nbar_i K_i / D)
+    const double ra = fast_rcp(alpha);
+    amin = fmin(amin, alpha);
+    x[i] *= ra;                  // z_i
+    v[i] = (pw[i] * rD2) * ra;   // v_i
+    qv = fma(K[i], v[i], qv);
+    qz = fma(K[i], x[i], qz);
+  }
+  const double hn = 1.0 - qv;
+  const double f = qz * fast_rcp(hn);
+  bool redo = false;
+  if (!(nonneg && (2.0 * kmax) * (pmax * rD2) < amin * hn)) {
+    // per-step test (rare): h_i by a running sum, suffix maximum of |p| from the back
+    double sfx[N], run = 0.0;
+    double m = 0.0;
+#pragma unroll
+    for (int s = N - 1; s >= 0; --s) {
+      sfx[s] = m;
+      m = fmax(m, fabs(pw[s]));
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double2 af = *reinterpret_cast<const double2*>(&sc[i].a0);
+      const double alpha = fma(af.y, rD, af.x);
+      const double h = 1.0 - run;
+      const double p = pw[i] * rD2;
+      const double dpiv = fabs(fma(alpha, h, -(p * K[i])));
+      redo |= !(h > 0.0) || (K[i] * (sfx[i] * rD2) > dpiv) || (dpiv == 0.0);
+      run = fma(K[i], v[i], run);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) x[i] = fma(v[i], f, x[i]);
+  return redo;
+}
+
 // Runtime n (9 .. kNMax): the same sweep over local arrays.
 template <int N>
 __device__ __forceinline__ bool structured_row(int n_rt, const SpeciesConst* sc, double cg, const double* c,
@@ -820,7 +889,11 @@ __global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_reside
         const uint32_t cc = live ? cell : nz - 1;  // idle lanes recompute the last cell, never store
         double k[CAP];
         if constexpr (ARITH == CHROM_KARITH_STRUCT && N > 0) {
+#ifdef CHROM_STRUCT_SWEEP
           const bool redo = structured_cell<N>(sc, cg, SRC, inlet + irow * n, nz, cc, k);
+#else
+          const bool redo = scan_cell<N>(sc, cg, SRC, inlet + irow * n, nz, cc, k);
+#endif
           if (redo) redo_mask |= 1u << ci;
           else if (live) bad |= apply_stage<N, false>(st, cc, k, n);
         } else {

@@ -1,0 +1,116 @@
+// multi_reg.cu — host side of the register-resident LangmuirMulti integrator (device code: multi_reg.cuh).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "kernels.h"
+
+namespace chrom {
+
+typedef void (*rkern_t)(const BatchDev);
+#define CHROM_DECL(N)                        \
+  rkern_t multi_reg_pick_##N(int method, int m); \
+  int multi_reg_tmax_##N(int m);
+CHROM_DECL(1) CHROM_DECL(2) CHROM_DECL(3) CHROM_DECL(4) CHROM_DECL(5) CHROM_DECL(6) CHROM_DECL(7) CHROM_DECL(8)
+#undef CHROM_DECL
+
+namespace {
+
+rkern_t lookup_reg(int n, int method, int m) {
+  switch (n) {
+    case 1: return multi_reg_pick_1(method, m);
+    case 2: return multi_reg_pick_2(method, m);
+    case 3: return multi_reg_pick_3(method, m);
+    case 4: return multi_reg_pick_4(method, m);
+    case 5: return multi_reg_pick_5(method, m);
+    case 6: return multi_reg_pick_6(method, m);
+    case 7: return multi_reg_pick_7(method, m);
+    case 8: return multi_reg_pick_8(method, m);
+  }
+  return nullptr;
+}
+
+int tmax_reg(int n, int m) {
+  switch (n) {
+    case 1: return multi_reg_tmax_1(m);
+    case 2: return multi_reg_tmax_2(m);
+    case 3: return multi_reg_tmax_3(m);
+    case 4: return multi_reg_tmax_4(m);
+    case 5: return multi_reg_tmax_5(m);
+    case 6: return multi_reg_tmax_6(m);
+    case 7: return multi_reg_tmax_7(m);
+    case 8: return multi_reg_tmax_8(m);
+  }
+  return 0;
+}
+
+}  // namespace
+
+// Cells per thread M in {1, 2, 4}; CHROM_REG_M overrides (experiments).
+bool multi_reg_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why) {
+  const int n = (int)b.n_species;
+  if (n < 1 || n > 8) {
+    if (why) *why = "register-resident multi kernel covers n_species 1..8";
+    return false;
+  }
+  const char* force = getenv("CHROM_REG_M");
+  int bestM = 0, bestT = 0;
+  // Measured on B200 (gpurun_out/multi_shapes_c.jsonl): a batch that fills the machine runs best with 2 cells per
+  // thread for n <= 4 and 1 for n >= 5 (register pressure); a batch that cannot fill it is latency-bound and wants
+  // the most threads per column (1 cell per thread).
+  const bool fills = (uint64_t)b.n_cols >= (uint64_t)sm_count * 2u;
+  const int order_small[3] = {2, 1, 4}, order_large[3] = {1, 2, 4}, order_latency[3] = {1, 2, 4};
+  const int* order = !fills ? order_latency : (n <= 4 ? order_small : order_large);
+  for (int oi = 0; oi < 3; ++oi) {
+    const int M = order[oi];
+    if (force && atoi(force) != M) continue;
+    const int tmax = std::abs(tmax_reg(n, M));
+    if (tmax == 0) continue;
+    const int T = (int)(((b.nz + M - 1) / M + 31u) / 32u * 32u);
+    if (T > tmax) continue;
+    bestM = M;
+    bestT = T;
+    break;
+  }
+  if (!bestM) {
+    if (why) *why = "column too long for the register-resident multi kernel (3*M*n doubles per thread)";
+    return false;
+  }
+  rkern_t k = lookup_reg(n, b.method, bestM);
+  if (!k) return false;
+  const size_t smem = tmax_reg(n, bestM) < 0 ? (size_t)bestM * n * bestT * sizeof(double) : 0;  // acc slots
+  if (smem > 48u * 1024u &&
+      cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, bestT, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  g->kind = 6;
+  g->M = bestM;
+  g->L = bestT;
+  g->cpw = 1;
+  g->warps_per_col = bestT / 32;
+  g->block = dim3(bestT);
+  g->cols_per_wave = (uint32_t)(sm_count * per_sm);
+  g->grid = dim3(std::min<uint32_t>(b.n_cols, g->cols_per_wave));
+  g->smem = smem;
+  char buf[240];
+  snprintf(buf, sizeof buf, "multi_reg<n=%d,%s,fast-scan-LU> threads/col=%d cells/thread=%d CTAs/SM=%d persistent grid=%u", n,
+           b.method == CHROM_RK4 ? "RK4" : "Euler", bestT, bestM, per_sm, g->grid.x);
+  g->name = buf;
+  return true;
+}
+
+cudaError_t multi_reg_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s) {
+  rkern_t k = lookup_reg((int)b.n_species, b.method, g.M);
+  if (!k) return cudaErrorInvalidValue;
+  const uint32_t grid = std::min<uint32_t>(b.n_cols, g.cols_per_wave ? g.cols_per_wave : b.n_cols);
+  k<<<dim3(grid), g.block, g.smem, s>>>(b);
+  return cudaGetLastError();
+}
+
+}  // namespace chrom

@@ -51,13 +51,12 @@ size_t multi_smem_bytes(int n, uint32_t nz) {
 
 }  // namespace
 
-// Resolves the kernel arithmetic of a multi-species batch: n > 8 has no register LU, so FAST maps to
-// the structured elimination there; CHROM_MULTI_STRUCT=1 opts n <= 8 into it as well.
+// Resolves the kernel arithmetic of a multi-species batch.  FAST (and FAST_STRUCTURED) = the closed-form
+// structured elimination for every n; FAST_DENSE = the dense register LU, which exists for n <= 8 only.
 int multi_kernel_arith(int n, int arith) {
   if (arith == CHROM_ARITH_EXACT) return arith;
-  if (arith == CHROM_KARITH_STRUCT || n > 8) return CHROM_KARITH_STRUCT;
-  const char* e = getenv("CHROM_MULTI_STRUCT");
-  return (e && atoi(e) != 0) ? CHROM_KARITH_STRUCT : CHROM_ARITH_FAST;
+  if (arith == CHROM_ARITH_FAST_DENSE && n <= 8) return CHROM_ARITH_FAST;  // kernel code 0 = dense register LU
+  return CHROM_KARITH_STRUCT;
 }
 
 // doubles of per-thread scratch the chosen kernel needs (0 for the register-only variants)

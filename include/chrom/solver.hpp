@@ -178,7 +178,8 @@ std::string validate_state_message(std::int64_t status);
 enum class Arithmetic : int {
   Fast = 0,            // CHROM_ARITH_FAST: FMA, one reciprocal per cell-stage; <= 1e-9 relative to the reference
   Exact = 1,           // CHROM_ARITH_EXACT: the reference's IEEE operations in the reference's order
-  FastStructured = 3,  // CHROM_ARITH_FAST_STRUCTURED (LangmuirMulti)
+  FastStructured = 3,  // CHROM_ARITH_FAST_STRUCTURED (LangmuirMulti: the explicit name of Fast)
+  FastDense = 4,       // CHROM_ARITH_FAST_DENSE (LangmuirMulti n <= 8: dense register LU with partial pivoting)
 };
 
 // One libchrom_cuda context (devices + streams).  Shared between solvers; calls are serialised.

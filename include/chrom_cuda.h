@@ -47,11 +47,15 @@ extern "C" {
  *         to the reference arithmetic (n<=4 closed-form inverses and n>=5 nalgebra LU included). */
 #define CHROM_ARITH_FAST 0
 #define CHROM_ARITH_EXACT 1
-/* LangmuirMulti only: FAST arithmetic with the LU of I + Fe*M = diag(alpha) - p q^T carried out on
- * the O(n) scalars that define it (same pivots, same partial-pivoting test; a cell that needs a row
- * exchange is redone with the dense LU).  The default FAST mode uses the dense register LU for
- * n <= 8 and this mode for n > 8. */
+/* LangmuirMulti.  I + Fe*M = diag(alpha) - p q^T (langmuir_multi.rs:655-663), so its LU with partial pivoting
+ * needs only the O(n) scalars that define it: FAST evaluates that elimination in closed form (same pivots, same
+ * partial-pivoting test; a cell that needs a row exchange is redone with the dense row-exchanging LU).
+ * CHROM_ARITH_FAST_STRUCTURED is the explicit name of that mode (= FAST for LangmuirMulti).
+ * CHROM_ARITH_FAST_DENSE forms the n x n matrix per cell and factorises it with a dense register-resident
+ * per-thread LU with partial pivoting (n <= 8; larger n run FAST): the same solution to rounding, more
+ * arithmetic, kept selectable because it is the literal algorithm and the pivoting fallback of FAST. */
 #define CHROM_ARITH_FAST_STRUCTURED 3
+#define CHROM_ARITH_FAST_DENSE 4
 
 #define CHROM_INJ_NONE 0
 #define CHROM_INJ_DIRAC 1     /* p0 = time, p1 = amount */
@@ -84,7 +88,7 @@ typedef struct {
 
 typedef struct {
   int32_t method;           /* CHROM_EULER | CHROM_RK4 */
-  int32_t arith;            /* CHROM_ARITH_FAST | CHROM_ARITH_EXACT */
+  int32_t arith;            /* CHROM_ARITH_FAST | CHROM_ARITH_EXACT (| _FAST_STRUCTURED | _FAST_DENSE: LangmuirMulti) */
   double total_time;        /* > 0 */
   uint64_t time_steps;      /* > 0; dt = total_time / (double)time_steps */
   uint32_t n_points;        /* nz >= 2 */

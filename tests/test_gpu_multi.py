@@ -102,7 +102,7 @@ def test_species_counts_exact_and_fast(ctx, n, nz):
     assert r.status[0] == 0 and ref.n_singular == 0
     assert_bit_equal(r.snapshots[0].transpose(0, 2, 1), ref.trajectory[::40], f"n={n} nz={nz} snapshots")
     assert_bit_equal(r.outlet[0], ref.outlet, f"n={n} nz={nz} outlet")
-    for arith in (cb.ARITH_FAST, cb.ARITH_FAST_STRUCTURED):
+    for arith in (cb.ARITH_FAST, cb.ARITH_FAST_DENSE):
         f = run_gpu(ctx, [m], cb.RK4, T, steps, arith, y0=y0_dev)
         assert max_rel_err(f.final_state[0].T, ref.final_state) <= PROFILE_RTOL
         assert max_rel_err(f.outlet[0], ref.outlet) <= PROFILE_RTOL
@@ -165,7 +165,7 @@ def test_partial_pivoting_is_exercised(ctx, n):
     r = run_gpu(ctx, [m], cb.RK4, T, steps, cb.ARITH_EXACT, y0=y0_dev)
     assert r.status[0] == 0 and ref.status == 0
     assert_bit_equal(r.final_state[0].T, ref.final_state, f"n={n} pivoting, exact")
-    for arith in (cb.ARITH_FAST, cb.ARITH_FAST_STRUCTURED):  # structured: pivot test fires -> dense redo
+    for arith in (cb.ARITH_FAST, cb.ARITH_FAST_DENSE):  # structured: pivot test fires -> dense redo
         f = run_gpu(ctx, [m], cb.RK4, T, steps, arith, y0=y0_dev)
         assert max_rel_err(f.final_state[0].T, ref.final_state) <= PROFILE_RTOL
 
@@ -179,7 +179,7 @@ def test_c5_shaped_batch(ctx):
     assert not r.status.any() and not ost.any()
     assert_bit_equal(r.final_state, of, "final")
     assert_bit_equal(r.outlet, oo, "outlet")
-    for arith in (cb.ARITH_FAST, cb.ARITH_FAST_STRUCTURED):
+    for arith in (cb.ARITH_FAST, cb.ARITH_FAST_DENSE):
         f = run_gpu(ctx, models, cb.RK4, T, steps, arith)
         assert max_rel_err(f.final_state, of) <= PROFILE_RTOL
     many = W.multi_batch_models(700, 8, 64, seed=3)  # more columns than persistent CTAs: the column loop

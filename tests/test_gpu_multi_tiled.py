@@ -63,7 +63,7 @@ def test_forced_tiles_thread_per_cell(ctx, monkeypatch, n, method, fuse):
         assert_bit_equal(r.snapshots[c].transpose(0, 2, 1), ref.trajectory[::7], f"n={n} snapshots col {c}")
         assert_bit_equal(r.outlet[c], ref.outlet, f"n={n} outlet col {c}")
         assert_bit_equal(r.final_state[c].T, ref.final_state, f"n={n} final col {c}")
-    for arith in (cb.ARITH_FAST, cb.ARITH_FAST_STRUCTURED):
+    for arith in (cb.ARITH_FAST, cb.ARITH_FAST_DENSE):
         f = run_gpu(ctx, [m], method, T, steps, arith, y0=y0_dev, want_summary=True)
         assert max_rel_err(f.final_state[0].T, ref.final_state) <= PROFILE_RTOL
         assert max_rel_err(f.outlet[0], ref.outlet) <= PROFILE_RTOL
