@@ -477,8 +477,8 @@ template <int N>
 __device__ __forceinline__ bool scan_cell(const SpeciesConst* sc, double cg, const double* SRC, const double* inlet_row,
                                           uint32_t nz, uint32_t cc, double (&x)[N]) {
   double K[N], pw[N], v[N];
-  double S = 0.0, pmax = 0.0, kmax = 0.0;
-  bool nonneg = true;
+  double S = 0.0, kmax = 0.0;
+  unsigned pmax_hi = 0u;  // integer max over the high words: negative / non-finite entries read as huge
 #pragma unroll
   for (int s = 0; s < N; ++s) {
     const double c = SRC[(size_t)s * nz + cc];
@@ -488,10 +488,11 @@ __device__ __forceinline__ bool scan_cell(const SpeciesConst* sc, double cg, con
     x[s] = (c - up) * cg;
     S = fma(kf.x, c, S);
     pw[s] = kf.y * c;  // feNK_s * c_s; p_s = pw_s / D^2
-    pmax = fmax(pmax, fabs(pw[s]));
+    pmax_hi = max(pmax_hi, (unsigned)__double2hiint(pw[s]));
     kmax = fmax(kmax, kf.x);
-    nonneg &= (__double2hiint(pw[s]) >= 0);
   }
+  const bool nonneg = pmax_hi < 0x7ff00000u;
+  const double pmax = __hiloint2double((int)(pmax_hi + 1u), 0);  // upper bound of max |feNK c|
   const double rD = fast_rcp(1.0 + S);
   const double rD2 = rD * rD;
   double qv = 0.0, qz = 0.0, amin = 1e300;

@@ -6,10 +6,13 @@
 // multi_kernels.cuh moves ~110 shared-memory wavefronts per warp and cell-stage (c, upstream, y, acc in; stage
 // state, acc out; species constants) and is bound by that pipe, not by FP64.  Here a thread owns M CONTIGUOUS
 // cells with y, acc and the stage state u of all n species in registers (3*M*n doubles), exactly the scheme of
-// single_resident.cu: cells are updated in descending order so the stage state is overwritten in place, the
-// upstream neighbour of a thread's first cell comes from the previous lane by shuffle (n 64-bit shuffles per
-// stage) and crosses warps through a 32*n-double shared array with ONE __syncthreads per stage.  Shared memory
-// then only carries the species constants (broadcast loads), the inlet row and the outlet summary.
+// single_resident.cu: cells are updated in descending order so the stage state is overwritten in place.  The
+// upstream neighbour of a thread's first cell is the previous thread's last cell: every thread posts that cell
+// (n doubles) to a double-buffered shared array xch[parity][species][thread + 1], slot 0 holding the inlet, and
+// reads slot `thread` after the ONE __syncthreads of the stage: n stores + n loads, conflict-free, no lane
+// special-casing (a shuffle would cost 2 instructions per double plus the warp-boundary handling).  Shared memory
+// otherwise only carries the species constants (broadcast loads), the inlet row, the outlet summary and, for the
+// wider shapes, the per-thread slots of the running slope acc.
 //
 // Per cell the solve is scan_row: the elimination of A = diag(alpha) - p q^T in closed form (pivot
 // alpha_i - p_i q_i / h_i, h_i = 1 - sum_{j<i} p_j q_j / alpha_j; x = z + v (q.z)/(1 - q.v)), n independent
@@ -17,6 +20,13 @@
 // with a cell that needs a row exchange redoes it with the dense row-exchanging register LU (fast_row).
 #pragma once
 #include "multi_kernels.cuh"
+
+#ifndef CHROM_REG_XCH_SMEM
+#define CHROM_REG_XCH_SMEM 0  // 1: every thread posts its last cell to shared memory instead of shuffling (measured slower at n = 8)
+#endif
+#ifndef CHROM_REG_DELAY_CONST
+#define CHROM_REG_DELAY_CONST 0  // 1: fence the second sweep's constant loads behind rD (no fewer spills, measured)
+#endif
 
 namespace chrom {
 namespace {
@@ -40,8 +50,9 @@ template <int N>
 __device__ __forceinline__ bool scan_row(const SpeciesConst* sc, double cg, double kmax, double a0min,
                                          const double (&c)[N], const double (&up)[N], double (&x)[N]) {
   double pv[N];  // feNK_s c_s, then v_s = p_s / alpha_s
-  double S0 = 0.0, S1 = 0.0, pmax = 0.0;
-  int sign = 0;
+  double S0 = 0.0, S1 = 0.0;
+  unsigned pmax_hi = 0u;  // max over the HIGH WORDS of feNK_s c_s, as unsigned: one integer max per species (a
+                          // double max costs 6 instructions here); a negative or non-finite entry reads as huge
 #pragma unroll
   for (int s = 0; s < N; ++s) {
     const double2 kf = *reinterpret_cast<const double2*>(&sc[s].K);  // {K, feNK}
@@ -49,18 +60,25 @@ __device__ __forceinline__ bool scan_row(const SpeciesConst* sc, double cg, doub
     if (s & 1) S1 = fma(kf.x, c[s], S1);
     else S0 = fma(kf.x, c[s], S0);
     pv[s] = kf.y * c[s];
-    pmax = fmax(pmax, fabs(pv[s]));
-    sign |= __double2hiint(pv[s]);
+    pmax_hi = max(pmax_hi, (unsigned)__double2hiint(pv[s]));
   }
   const double rD = fast_rcp(1.0 + (S0 + S1));
   const double rD2 = rD * rD;
-  const double pmax2 = pmax * rD2;  // max_r |p_r|
+  // upper bound of max_r |p_r| (next high word up); all c >= 0 iff the sign bit is clear
+  const bool nonneg = pmax_hi < 0x7ff00000u;
+  const double pmax2 = __hiloint2double((int)(pmax_hi + 1u), 0) * rD2;
   double qv0 = 0.0, qv1 = 0.0, qz0 = 0.0, qz1 = 0.0;
+  // The second sweep's constants must not be fetched before rD exists: hoisted to the top of the stage they would
+  // hold 3n more registers across the first sweep and push y into local memory.
+  const SpeciesConst* sc2 = sc;
+#if CHROM_REG_DELAY_CONST
+  asm volatile("" : "+l"(sc2) : "d"(rD));
+#endif
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const double2 af = *reinterpret_cast<const double2*>(&sc[i].a0);  // {a0, feNK}
-    const double ra = fast_rcp(fma(af.y, rD, af.x));                   // 1 / alpha_i
-    const double Ki = sc[i].K;
+    const double2 af = *reinterpret_cast<const double2*>(&sc2[i].a0);  // {a0, feNK}
+    const double ra = fast_rcp(fma(af.y, rD, af.x));                    // 1 / alpha_i
+    const double Ki = sc2[i].K;
     x[i] *= ra;                   // z_i
     pv[i] = (pv[i] * rD2) * ra;   // v_i
     if (i & 1) {
@@ -76,7 +94,7 @@ __device__ __forceinline__ bool scan_row(const SpeciesConst* sc, double cg, doub
   bool redo = false;
   // Sufficient for "no row exchange anywhere": 2 max q max|p| < min alpha (1 - q.v), with alpha_i >= a0_i when
   // every c >= 0 (h_i >= h_n then).  Anything else takes the per-step test.
-  if (!(sign >= 0 && (2.0 * kmax) * pmax2 < a0min * hn)) {
+  if (!(nonneg && (2.0 * kmax) * pmax2 < a0min * hn)) {
     double run = 0.0;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -101,11 +119,18 @@ __device__ __forceinline__ bool scan_row(const SpeciesConst* sc, double cg, doub
   return redo;
 }
 
-// dense row-exchanging register LU for a flagged cell, out of line (its matrix must not inflate the hot path)
+// dense row-exchanging register LU for a flagged cell, out of line (its matrix must not inflate the hot path).
+// Operands and result travel BY VALUE: no array of the hot path ever has its address taken.
 template <int N>
-__device__ __noinline__ void cold_row(const SpeciesConst* sc, double fe, double cg, const double* c, const double* up,
-                                      double* k) {
-  fast_row<N>(sc, fe, cg, c, up, k);  // warp-synchronous inside (pivot votes): called by whole warps
+struct VecN {
+  double v[N];
+};
+
+template <int N>
+__device__ __noinline__ VecN<N> cold_row(const SpeciesConst* sc, double fe, double cg, const VecN<N> c, const VecN<N> up) {
+  VecN<N> k;
+  fast_row<N>(sc, fe, cg, c.v, up.v, k.v);  // warp-synchronous inside (pivot votes): called by whole warps
+  return k;
 }
 
 template <int N, int M, int METHOD>
@@ -113,14 +138,13 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
   constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
   __shared__ SpeciesConst sc[N];
   __shared__ double inlet[2][3][N];   // [step parity][stage row][species]
-  __shared__ double halo[2][32][N];   // [stage parity][warp][species]: the last cell of each warp
   __shared__ double summ[N][5];       // area, moment, max, tmax, previous sample (outlet owner only)
   __shared__ const double* tabs[N];
   __shared__ double colc[2];          // max_i K_i, min_i (1 + fe lambda_i) of the current column
   constexpr bool ACC_SH = reg_acc_shared(N, M);
-  extern __shared__ double acc_sh[];  // ACC_SH: [M][N][blockDim.x], thread-private slots (conflict-free)
+  extern __shared__ double dyn_sh[];  // xch[2][N][T + 1], then (ACC_SH) acc[M][N][T]: thread-private slots
 
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const uint32_t nz = b.nz;
   const int cell0 = tid * M;
   const int nv = max(0, min(M, (int)nz - cell0));  // real cells of this thread
@@ -151,8 +175,9 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
       tabs[tid] = b.tables + (size_t)sp.inj_table * steps * ST;
     }
     double y[M][N], u[M][N], acc[ACC_SH ? 1 : M][ACC_SH ? 1 : N];
-    double* const my_acc = acc_sh + tid;
     const int T = blockDim.x;
+    double* const xch = dyn_sh;                                  // [2][N][T + 1] (shuffle variant: [2][N][33])
+    double* const my_acc = dyn_sh + 2 * N * (T + 1) + tid;       // [M][N][T]
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
@@ -205,33 +230,47 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
     // (0 Euler; 1..4 RK4).  src/dst are register arrays; stages 2-4 run in place on u.
     auto stage = [&](double (&src)[M][N], int irow, int spar, int par, int which) {
       double upx[N];
+#if CHROM_REG_XCH_SMEM
+      double* const post = xch + (size_t)par * N * (T + 1);
+#pragma unroll
+      for (int s = 0; s < N; ++s) post[s * (T + 1) + tid + 1] = src[M - 1][s];
+      if (tid < N) post[tid * (T + 1)] = inlet[spar][irow][tid];  // slot 0: the inlet of this stage
+      __syncthreads();
+#pragma unroll
+      for (int s = 0; s < N; ++s) upx[s] = post[s * (T + 1) + tid];
+#else
+      // previous lane by shuffle; warp boundaries through xch[par][species][warp + 1], slot 0 = the inlet
+      double* const post = xch + (size_t)par * N * 33;
+      const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
       for (int s = 0; s < N; ++s) {
         const double last = src[M - 1][s];
         upx[s] = __shfl_up_sync(0xffffffffu, last, 1);
-        if (lane == 31) halo[par][warp][s] = last;
+        if (lane == 31) post[s * 33 + warp + 1] = last;
       }
+      if (tid < N) post[tid * 33] = inlet[spar][irow][tid];
       __syncthreads();
       if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < N; ++s) upx[s] = (warp > 0) ? halo[par][warp - 1][s] : inlet[spar][irow][s];
+        for (int s = 0; s < N; ++s) upx[s] = post[s * 33 + warp];
       }
+#endif
 #pragma unroll
       for (int j = M - 1; j >= 0; --j) {
         double k[N], upv[N];
 #pragma unroll
         for (int s = 0; s < N; ++s) upv[s] = (j > 0) ? src[j - 1][s] : upx[s];
         const bool redo = scan_row<N>(sc, cg, colc[0], colc[1], src[j], upv, k);
-        if (__any_sync(0xffffffffu, redo)) {  // copies: only these temporaries may live in local memory
-          double cc[N], uu[N], kk[N];
+        if (__any_sync(0xffffffffu, redo)) {
+          VecN<N> cc, uu;
 #pragma unroll
           for (int s = 0; s < N; ++s) {
-            cc[s] = src[j][s];
-            uu[s] = upv[s];
+            cc.v[s] = src[j][s];
+            uu.v[s] = upv[s];
           }
-          cold_row<N>(sc, fe, cg, cc, uu, kk);
+          const VecN<N> kk = cold_row<N>(sc, fe, cg, cc, uu);
 #pragma unroll
-          for (int s = 0; s < N; ++s) k[s] = kk[s];
+          for (int s = 0; s < N; ++s) k[s] = kk.v[s];
         }
 #pragma unroll
         for (int s = 0; s < N; ++s) {
