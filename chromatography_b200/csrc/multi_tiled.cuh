@@ -143,15 +143,21 @@ __device__ __noinline__ void warp_dense_fast(int n, const SpeciesConst* sc, doub
   }
 }
 
-// ---- warp per cell, FAST: the structured elimination as scans ------------------------------------------
+// ---- warp per cell, FAST: the structured elimination in closed form ---------------------------------------
 // Lane `lane` holds species lane + 32*j, j < WJ.  K/feNK/a0 are the lane's species constants (cached in
-// registers for the whole tile).  C cells are solved side by side: their shuffle chains are independent, so
-// interleaving them hides the shuffle / reciprocal latency a single cell would expose.
+// registers for the whole tile); kmax = max_i K_i and a0min = min_i (1 + fe lambda_i) of the column.  C cells
+// are solved side by side: their shuffle chains are independent, so interleaving them hides the shuffle /
+// reciprocal latency a single cell would expose.
+// Solution: x = z + v (q.z)/(1 - q.v), z = b/alpha, v = p/alpha — three butterfly reductions (S, q.v, q.z).
+// Partial pivoting: a sufficient bound, 2 max q max|p| < min alpha (1 - q.v) with every c >= 0 (one integer
+// REDUX over the high words), rules a row exchange out for the whole cell; only a cell that fails it runs the
+// per-step test (exclusive prefix sums h_i and suffix maxima of |p| by warp scans).
 // Returns the (warp-uniform) mask of cells where partial pivoting would exchange rows (their k[] is invalid).
 template <int WJ, int C>
 __device__ __forceinline__ unsigned warp_cells_fast(int n, int lane, const double (&K)[WJ], const double (&feNK)[WJ],
-                                                    const double (&a0)[WJ], double cg, const double (&c)[C][WJ],
-                                                    const double (&up)[C][WJ], double (&k)[C][WJ]) {
+                                                    const double (&a0)[WJ], double kmax, double a0min, double cg,
+                                                    const double (&c)[C][WJ], const double (&up)[C][WJ],
+                                                    double (&k)[C][WJ]) {
   double S[C];
 #pragma unroll
   for (int q = 0; q < C; ++q) {
@@ -163,81 +169,87 @@ __device__ __forceinline__ unsigned warp_cells_fast(int n, int lane, const doubl
   for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
     for (int q = 0; q < C; ++q) S[q] += __shfl_xor_sync(kFull, S[q], o);
-  double rD[C], rD2[C], run[C], qz[C];
+  double rD[C], rD2[C], qv[C], qz[C];
+  double p[C][WJ], z[C][WJ], v[C][WJ];
+  unsigned phi[C];  // max over the high words of feNK c (unsigned: a negative or non-finite entry reads as huge)
 #pragma unroll
   for (int q = 0; q < C; ++q) {
     rD[q] = fast_rcp(1.0 + S[q]);
     rD2[q] = rD[q] * rD[q];
-    run[q] = 0.0;
+    qv[q] = 0.0;
     qz[q] = 0.0;
-  }
-  double p[C][WJ], alpha[C][WJ], z[C][WJ], v[C][WJ], h[C][WJ];
+    phi[q] = 0u;
 #pragma unroll
-  for (int j = 0; j < WJ; ++j) {
-    double incl[C];
-#pragma unroll
-    for (int q = 0; q < C; ++q) {
-      p[q][j] = feNK[j] * c[q][j] * rD2[q];          // fe nbar K c / D^2
-      alpha[q][j] = fma(feNK[j], rD[q], a0[j]);      // 1 + fe (lambda + nbar K / D)
-      const double ra = fast_rcp(alpha[q][j]);
+    for (int j = 0; j < WJ; ++j) {
+      const double pw = feNK[j] * c[q][j];
+      phi[q] = max(phi[q], (unsigned)__double2hiint(pw));
+      p[q][j] = pw * rD2[q];                                  // fe nbar K c / D^2
+      const double ra = fast_rcp(fma(feNK[j], rD[q], a0[j]));  // 1 / alpha, alpha = 1 + fe (lambda + nbar K / D)
       z[q][j] = (c[q][j] - up[q][j]) * cg * ra;
       v[q][j] = p[q][j] * ra;
-      incl[q] = K[j] * v[q][j];                      // p_i q_i / alpha_i
+      qv[q] = fma(K[j], v[q][j], qv[q]);
       qz[q] = fma(K[j], z[q][j], qz[q]);
-    }
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)                 // inclusive scan over the 32 species of block j
-#pragma unroll
-      for (int q = 0; q < C; ++q) {
-        const double u = __shfl_up_sync(kFull, incl[q], o);
-        if (lane >= o) incl[q] += u;
-      }
-#pragma unroll
-    for (int q = 0; q < C; ++q) {
-      double excl = __shfl_up_sync(kFull, incl[q], 1);
-      if (lane == 0) excl = 0.0;
-      h[q][j] = 1.0 - (run[q] + excl);               // h_i = 1 - sum_{r<i} p_r q_r / alpha_r
-      run[q] += __shfl_sync(kFull, incl[q], 31);
-    }
-  }
-  // partial-pivoting test: q_i * max_{r>i} |p_r|  >  |alpha_i h_i - p_i q_i|   (h_i > 0)
-  unsigned redo = 0u;
-  double runmax[C];
-#pragma unroll
-  for (int q = 0; q < C; ++q) runmax[q] = 0.0;
-#pragma unroll
-  for (int j = WJ - 1; j >= 0; --j) {
-    double sfx[C];  // inclusive suffix maximum inside block j
-#pragma unroll
-    for (int q = 0; q < C; ++q) sfx[q] = fabs(p[q][j]);
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-#pragma unroll
-      for (int q = 0; q < C; ++q) {
-        const double u = __shfl_down_sync(kFull, sfx[q], o);
-        if (lane + o < 32) sfx[q] = fmax(sfx[q], u);
-      }
-#pragma unroll
-    for (int q = 0; q < C; ++q) {
-      double excl = __shfl_down_sync(kFull, sfx[q], 1);
-      if (lane == 31) excl = 0.0;
-      const double below = fmax(runmax[q], excl);
-      runmax[q] = fmax(runmax[q], __shfl_sync(kFull, sfx[q], 0));
-      if (lane + 32 * j < n) {
-        const double dpiv = fabs(fma(alpha[q][j], h[q][j], -(p[q][j] * K[j])));
-        if (!(h[q][j] > 0.0) || (K[j] * below > dpiv) || (dpiv == 0.0)) redo |= 1u << q;
-      }
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-    for (int q = 0; q < C; ++q) qz[q] += __shfl_xor_sync(kFull, qz[q], o);
+    for (int q = 0; q < C; ++q) {
+      qv[q] += __shfl_xor_sync(kFull, qv[q], o);
+      qz[q] += __shfl_xor_sync(kFull, qz[q], o);
+    }
+  unsigned suspect = 0u;  // warp-uniform
 #pragma unroll
   for (int q = 0; q < C; ++q) {
-    const double f = qz[q] * fast_rcp(1.0 - run[q]);  // (q.z) / (1 - q.v)
+    const double hn = 1.0 - qv[q];
+    const double f = qz[q] * fast_rcp(hn);  // (q.z) / (1 - q.v)
 #pragma unroll
     for (int j = 0; j < WJ; ++j) k[q][j] = fma(v[q][j], f, z[q][j]);
+    const unsigned pmax_hi = __reduce_max_sync(kFull, phi[q]);
+    const double pmax = __hiloint2double((int)(pmax_hi + 1u), 0) * rD2[q];  // upper bound of max_r |p_r|
+    if (!(pmax_hi < 0x7ff00000u && (2.0 * kmax) * pmax < a0min * hn)) suspect |= 1u << q;
+  }
+  if (suspect == 0u) return 0u;
+
+  // ---- rare: the per-step partial-pivoting test, q_i * max_{r>i}|p_r| > |alpha_i h_i - p_i q_i| (h_i > 0) ----
+  unsigned redo = 0u;
+#pragma unroll
+  for (int q = 0; q < C; ++q) {
+    if (!((suspect >> q) & 1u)) continue;  // warp-uniform
+    double h[WJ], run = 0.0;
+#pragma unroll
+    for (int j = 0; j < WJ; ++j) {  // h_i = 1 - sum_{r<i} p_r q_r / alpha_r: inclusive scan per block of 32 species
+      const double t = K[j] * v[q][j];
+      double incl = t;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += u;
+      }
+      double excl = __shfl_up_sync(kFull, incl, 1);
+      if (lane == 0) excl = 0.0;
+      h[j] = 1.0 - (run + excl);
+      run += __shfl_sync(kFull, incl, 31);
+    }
+    double runmax = 0.0;
+#pragma unroll
+    for (int j = WJ - 1; j >= 0; --j) {
+      double sfx = fabs(p[q][j]);  // inclusive suffix maximum inside block j
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double u = __shfl_down_sync(kFull, sfx, o);
+        if (lane + o < 32) sfx = fmax(sfx, u);
+      }
+      double excl = __shfl_down_sync(kFull, sfx, 1);
+      if (lane == 31) excl = 0.0;
+      const double below = fmax(runmax, excl);
+      runmax = fmax(runmax, __shfl_sync(kFull, sfx, 0));
+      if (lane + 32 * j < n) {
+        const double alpha = fma(feNK[j], rD[q], a0[j]);
+        const double dpiv = fabs(fma(alpha, h[j], -(p[q][j] * K[j])));
+        if (!(h[j] > 0.0) || (K[j] * below > dpiv) || (dpiv == 0.0)) redo |= 1u << q;
+      }
+    }
   }
   return __reduce_or_sync(kFull, redo);
 }
@@ -450,14 +462,24 @@ __global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi
       }
     // warp per cell: the lane's species constants stay in registers for the whole tile
     double wK[WJC], wF[WJC], wA[WJC];
+    double w_kmax = 0.0, w_a0min = 0.0;  // max_i K_i and min_i (1 + fe lambda_i) of the column (pivot bound)
     if (WJ > 0) {
+      unsigned kh = 0u, ah = 0xffffffffu;
 #pragma unroll
       for (int j = 0; j < WJC; ++j) {
         const int s = lane + 32 * j;
         wK[j] = (s < n) ? sc[s].K : 0.0;
         wF[j] = (s < n) ? sc[s].feNK : 0.0;
         wA[j] = (s < n) ? sc[s].a0 : 1.0;
+        if (s < n) {  // positive constants: the high words order like the doubles
+          kh = max(kh, (unsigned)__double2hiint(wK[j]));
+          ah = min(ah, (unsigned)__double2hiint(wA[j]));
+        }
       }
+      kh = __reduce_max_sync(kFull, kh);
+      ah = __reduce_min_sync(kFull, ah);
+      w_kmax = __hiloint2double((int)(kh + 1u), 0);  // rounded up / down: the bound stays sufficient
+      w_a0min = __hiloint2double((int)ah, 0);
     }
 
     // One stage over the tile.  Returns the non-finite flag of the cells this tile owns.
@@ -492,7 +514,7 @@ __global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi
                 up[q][j] = (s < n) ? ((cc > 0) ? SRC[(size_t)s * pitch + cc - 1] : inlet_row[s]) : 0.0;
               }
             }
-            const unsigned redo = warp_cells_fast<WJC, C>(n, lane, wK, wF, wA, cg, c, up, k);
+            const unsigned redo = warp_cells_fast<WJC, C>(n, lane, wK, wF, wA, w_kmax, w_a0min, cg, c, up, k);
 #pragma unroll
             for (int q = 0; q < C; ++q) {
               const uint32_t cc = cc0 + (uint32_t)q;
