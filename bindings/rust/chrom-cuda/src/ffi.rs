@@ -7,6 +7,8 @@ pub const CHROM_EULER: i32 = 0;
 pub const CHROM_RK4: i32 = 1;
 pub const CHROM_ARITH_FAST: i32 = 0;
 pub const CHROM_ARITH_EXACT: i32 = 1;
+pub const CHROM_ARITH_FAST_STRUCTURED: i32 = 3; // LangmuirMulti: the explicit name of FAST
+pub const CHROM_ARITH_FAST_DENSE: i32 = 4; // LangmuirMulti n <= 8: dense register LU on every cell
 
 #[repr(C)]
 pub struct chrom_cuda_ctx {
@@ -69,6 +71,9 @@ unsafe extern "C" {
     pub fn chrom_cuda_status_message(status: i64, buf: *mut c_char, buf_len: usize) -> usize;
     pub fn chrom_cuda_host_alloc(bytes: usize, out: *mut *mut c_void) -> i32;
     pub fn chrom_cuda_host_free(p: *mut c_void);
+    pub fn chrom_cuda_bind_host_thread(
+        ctx: *mut chrom_cuda_ctx, device_index: i32, numa_node: *mut i32, n_cpus: *mut i32,
+    ) -> i32;
     pub fn chrom_cuda_solve_single_batch(
         ctx: *mut chrom_cuda_ctx, cfg: *const chrom_run_cfg, cols: *const chrom_single_col, n_cols: u64,
         inj_tables: *const f64, n_tables: u32, y0: *const f64, outlet: *mut f64, snapshots: *mut f64,
