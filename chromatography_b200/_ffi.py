@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libchrom_cuda.so")
+# CHROM_CUDA_LIB: another build of the same library (kernel A/B experiments); default: the in-tree build
+LIB_PATH = os.environ.get("CHROM_CUDA_LIB") or os.path.join(_HERE, "libchrom_cuda.so")
 
 CHROM_OK = 0
 CHROM_ERR_INVALID, CHROM_ERR_CUDA, CHROM_ERR_UNSUPPORTED, CHROM_ERR_NO_DEVICE = -1, -2, -3, -4

@@ -78,8 +78,9 @@ bool multi_reg_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::strin
   }
   rkern_t k = lookup_reg(n, b.method, bestM);
   if (!k) return false;
-  // neighbour exchange xch[2][n][T + 1], then the acc slots [M][n][T] where acc lives in shared memory
-  const size_t smem = ((size_t)2 * n * (bestT + 1) + (tmax_reg(n, bestM) < 0 ? (size_t)bestM * n * bestT : 0)) * sizeof(double);
+  // neighbour exchange xch[2][T + 1][n | 1], then the acc slots [T][(M n) | 1] where acc lives in shared memory
+  const size_t smem = ((size_t)2 * (bestT + 1) * (n | 1) +
+                       (tmax_reg(n, bestM) < 0 ? (size_t)bestT * ((bestM * n) | 1) : 0)) * sizeof(double);
   if (smem > 48u * 1024u &&
       cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     cudaGetLastError();

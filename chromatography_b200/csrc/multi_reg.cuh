@@ -22,7 +22,7 @@
 #include "multi_kernels.cuh"
 
 #ifndef CHROM_REG_XCH_SMEM
-#define CHROM_REG_XCH_SMEM 0  // 1: every thread posts its last cell to shared memory instead of shuffling (measured slower at n = 8)
+#define CHROM_REG_XCH_SMEM 1  // 1: every thread posts its last cell to shared memory (C5 658 ms); 0: shuffle + warp-boundary slots (693 ms)
 #endif
 #ifndef CHROM_REG_DELAY_CONST
 #define CHROM_REG_DELAY_CONST 0  // 1: fence the second sweep's constant loads behind rD (no fewer spills, measured)
@@ -47,7 +47,8 @@ constexpr int reg_max_threads(int N, int M) {
 
 // scan_cell of multi_kernels.cuh on register operands.  Returns true when the cell needs a row exchange.
 template <int N>
-__device__ __forceinline__ bool scan_row(const SpeciesConst* sc, double cg, double kmax, double a0min,
+// x solves A x = c - up: the factor -ue/dz of the right-hand side is folded into the stage coefficients by the caller.
+__device__ __forceinline__ bool scan_row(const SpeciesConst* sc, double kmax, double a0min,
                                          const double (&c)[N], const double (&up)[N], double (&x)[N]) {
   double pv[N];  // feNK_s c_s, then v_s = p_s / alpha_s
   double S0 = 0.0, S1 = 0.0;
@@ -56,7 +57,7 @@ __device__ __forceinline__ bool scan_row(const SpeciesConst* sc, double cg, doub
 #pragma unroll
   for (int s = 0; s < N; ++s) {
     const double2 kf = *reinterpret_cast<const double2*>(&sc[s].K);  // {K, feNK}
-    x[s] = (c[s] - up[s]) * cg;
+    x[s] = c[s] - up[s];
     if (s & 1) S1 = fma(kf.x, c[s], S1);
     else S0 = fma(kf.x, c[s], S0);
     pv[s] = kf.y * c[s];
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
   __shared__ const double* tabs[N];
   __shared__ double colc[2];          // max_i K_i, min_i (1 + fe lambda_i) of the current column
   constexpr bool ACC_SH = reg_acc_shared(N, M);
-  extern __shared__ double dyn_sh[];  // xch[2][N][T + 1], then (ACC_SH) acc[M][N][T]: thread-private slots
+  extern __shared__ double dyn_sh[];  // xch[2][T + 1][N | 1], then (ACC_SH) acc[T][(M * N) | 1]
 
   const int tid = threadIdx.x;
   const uint32_t nz = b.nz;
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
     const chrom_multi_col cp = b.mcols[col];
     const double fe = cp.fe;
     const double cg = -cp.ue / cp.dz;
+    const double cdt = cg * dt, ch2 = cg * h2, ch6 = cg * h6;  // k is solved without the factor -ue/dz (scan_row)
     __syncthreads();  // the previous column's readers of shared memory are done
     if (tid < N) {
       const chrom_species sp = b.species[cp.species_off + tid];
@@ -176,8 +178,12 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
     }
     double y[M][N], u[M][N], acc[ACC_SH ? 1 : M][ACC_SH ? 1 : N];
     const int T = blockDim.x;
-    double* const xch = dyn_sh;                                  // [2][N][T + 1] (shuffle variant: [2][N][33])
-    double* const my_acc = dyn_sh + 2 * N * (T + 1) + tid;       // [M][N][T]
+    // Shared-memory layouts keep the species index fastest with an ODD row stride (in doubles): a thread's row is
+    // addressed with compile-time offsets from one base register and consecutive lanes hit distinct banks.
+    constexpr int XS = N | 1;        // xch[2][T + 1][XS]: slot t + 1 = thread t's last cell, slot 0 = the inlet
+    constexpr int AS = (M * N) | 1;  // acc[T][AS] (ACC_SH): thread-private slots
+    double* const xch = dyn_sh;
+    double* const my_acc = dyn_sh + 2 * (T + 1) * XS + tid * AS;
 #pragma unroll
     for (int j = 0; j < M; ++j)
 #pragma unroll
@@ -231,16 +237,16 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
     auto stage = [&](double (&src)[M][N], int irow, int spar, int par, int which) {
       double upx[N];
 #if CHROM_REG_XCH_SMEM
-      double* const post = xch + (size_t)par * N * (T + 1);
+      double* const post = xch + ((size_t)par * (T + 1) + tid) * XS;  // row of slot `tid`; the thread's own row is next
 #pragma unroll
-      for (int s = 0; s < N; ++s) post[s * (T + 1) + tid + 1] = src[M - 1][s];
-      if (tid < N) post[tid * (T + 1)] = inlet[spar][irow][tid];  // slot 0: the inlet of this stage
+      for (int s = 0; s < N; ++s) post[XS + s] = src[M - 1][s];
+      if (tid < N) xch[(size_t)par * (T + 1) * XS + tid] = inlet[spar][irow][tid];  // slot 0: the inlet of this stage
       __syncthreads();
 #pragma unroll
-      for (int s = 0; s < N; ++s) upx[s] = post[s * (T + 1) + tid];
+      for (int s = 0; s < N; ++s) upx[s] = post[s];
 #else
       // previous lane by shuffle; warp boundaries through xch[par][species][warp + 1], slot 0 = the inlet
-      double* const post = xch + (size_t)par * N * 33;
+      double* const post = xch + (size_t)par * N * 33;  // [species][33]
       const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
       for (int s = 0; s < N; ++s) {
@@ -260,7 +266,7 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
         double k[N], upv[N];
 #pragma unroll
         for (int s = 0; s < N; ++s) upv[s] = (j > 0) ? src[j - 1][s] : upx[s];
-        const bool redo = scan_row<N>(sc, cg, colc[0], colc[1], src[j], upv, k);
+        const bool redo = scan_row<N>(sc, colc[0], colc[1], src[j], upv, k);
         if (__any_sync(0xffffffffu, redo)) {
           VecN<N> cc, uu;
 #pragma unroll
@@ -268,25 +274,25 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
             cc.v[s] = src[j][s];
             uu.v[s] = upv[s];
           }
-          const VecN<N> kk = cold_row<N>(sc, fe, cg, cc, uu);
+          const VecN<N> kk = cold_row<N>(sc, fe, 1.0, cc, uu);  // unscaled like scan_row
 #pragma unroll
           for (int s = 0; s < N; ++s) k[s] = kk.v[s];
         }
 #pragma unroll
         for (int s = 0; s < N; ++s) {
           if (which == 0) {
-            y[j][s] = fma(k[s], dt, y[j][s]);
+            y[j][s] = fma(k[s], cdt, y[j][s]);
           } else if (which == 1) {
-            if (ACC_SH) my_acc[(j * N + s) * T] = k[s];
+            if (ACC_SH) my_acc[j * N + s] = k[s];
             else acc[j][s] = k[s];
-            u[j][s] = fma(k[s], h2, y[j][s]);
+            u[j][s] = fma(k[s], ch2, y[j][s]);
           } else if (which == 2 || which == 3) {
-            if (ACC_SH) my_acc[(j * N + s) * T] = fma(k[s], 2.0, my_acc[(j * N + s) * T]);
+            if (ACC_SH) my_acc[j * N + s] = fma(k[s], 2.0, my_acc[j * N + s]);
             else acc[j][s] = fma(k[s], 2.0, acc[j][s]);
-            u[j][s] = fma(k[s], which == 2 ? h2 : dt, y[j][s]);
+            u[j][s] = fma(k[s], which == 2 ? ch2 : cdt, y[j][s]);
           } else {
-            const double a = ACC_SH ? my_acc[(j * N + s) * T] : acc[j][s];
-            y[j][s] = fma(a + k[s], h6, y[j][s]);
+            const double a = ACC_SH ? my_acc[j * N + s] : acc[j][s];
+            y[j][s] = fma(a + k[s], ch6, y[j][s]);
           }
         }
       }
