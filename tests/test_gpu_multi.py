@@ -222,3 +222,32 @@ def test_solver_trait_mirror_multi(ctx):
     assert_bit_equal(res.state_trajectory, ref.trajectory, "state_trajectory")
     assert_bit_equal(res.final_state, ref.final_state, "final_state")
     assert res.metadata["function evaluations"] == "2000"
+
+
+@pytest.mark.parametrize("nz", [2, 3, 31, 32, 33, 64, 65, 257])
+@pytest.mark.parametrize("n", [1, 3, 8])
+def test_ragged_grid_sizes(ctx, n, nz):
+    """Grid sizes around the warp / thread-tile boundaries (the smallest legal column has 2 cells): the register-
+    resident FAST kernel (1, 2 or 4 cells per thread), the dense-LU and the exact shared-memory kernels."""
+    steps, T = 30, 3.0
+    rng = np.random.default_rng(17 * n + nz)
+    y0 = rng.uniform(0.0, 0.05, size=(nz, n))
+    m = cb.LangmuirMulti.new(random_species(n, seed=n), nz, 0.4, 1e-3, 0.25 * nz / 100.0)
+    ref = O.solve_multi(to_oracle(m), O.RK4, T, steps, y0=y0, want_trajectory=True)
+    y0_dev = np.ascontiguousarray(y0.T)[None]
+    batch = [m] * 3  # three columns: the persistent-CTA column loop with a non-zero initial state
+    r = run_gpu(ctx, batch, cb.RK4, T, steps, cb.ARITH_EXACT, y0=np.repeat(y0_dev, 3, axis=0), snapshot_stride=10)
+    assert not r.status.any()
+    for c in range(3):
+        assert_bit_equal(r.snapshots[c].transpose(0, 2, 1), ref.trajectory[::10], f"n={n} nz={nz} snapshots")
+        assert_bit_equal(r.outlet[c], ref.outlet, f"n={n} nz={nz} outlet")
+    for arith in (cb.ARITH_FAST, cb.ARITH_FAST_DENSE):
+        f = run_gpu(ctx, batch, cb.RK4, T, steps, arith, y0=np.repeat(y0_dev, 3, axis=0), snapshot_stride=10,
+                    want_summary=True)
+        for c in range(3):
+            assert max_rel_err(f.snapshots[c].transpose(0, 2, 1), ref.trajectory[::10]) <= PROFILE_RTOL
+            assert max_rel_err(f.outlet[c], ref.outlet) <= PROFILE_RTOL
+            assert max_rel_err(f.final_state[c].T, ref.final_state) <= PROFILE_RTOL
+            for k in range(n):
+                area = O.trapezoid(ref.time_points, ref.outlet[k])
+                assert abs(f.summary[c][k][0] - area) <= MOMENT_RTOL * abs(area)
