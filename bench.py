@@ -319,6 +319,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
+    ap.add_argument("--pin-cpus", action="store_true", help="experiment: pin each local rank to its share of the CPUs")
     args = ap.parse_args()
 
     spec = workload_spec(args.workload)
@@ -346,6 +347,10 @@ def main():
     # (restored before the CPU baseline, which uses every host core)
     affinity0 = os.sched_getaffinity(0)
     numa = ctx.bind_host_thread(0) if not args.no_numa else (-1, 0)
+    if args.pin_cpus and world > 1:  # experiment: an equal share of the allowed CPUs per local rank
+        cpus = sorted(affinity0)
+        share = max(1, len(cpus) // world)
+        os.sched_setaffinity(0, set(cpus[local_rank * share:(local_rank + 1) * share]))
 
     n_cols = args.cols or spec["n_cols"]
     inp = build_inputs(spec, n_cols, rank)

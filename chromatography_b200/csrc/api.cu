@@ -500,7 +500,10 @@ int32_t chrom_cuda_last_timing(const chrom_cuda_ctx* ctx, chrom_cuda_timing* out
 int32_t chrom_cuda_host_alloc(size_t bytes, void** out) {
   if (!out) return CHROM_ERR_INVALID;
   *out = nullptr;
-  if (cudaHostAlloc(out, bytes, cudaHostAllocPortable) != cudaSuccess) {
+  unsigned flags = cudaHostAllocPortable;
+  if (const char* e = getenv("CHROM_HOST_WC"))  // write-combined pages: device->host DMA without CPU cache snooping
+    if (atoi(e) != 0) flags |= cudaHostAllocWriteCombined;
+  if (cudaHostAlloc(out, bytes, flags) != cudaSuccess) {
     cudaGetLastError();
     return CHROM_ERR_CUDA;
   }
