@@ -6,7 +6,7 @@
 // multi_kernels.cuh moves ~110 shared-memory wavefronts per warp and cell-stage (c, upstream, y, acc in; stage
 // state, acc out; species constants) and is bound by that pipe, not by FP64.  Here a thread owns M CONTIGUOUS
 // cells with y, acc and the stage state u of all n species in registers (3*M*n doubles), exactly the scheme of
-// single_resident.cu: cells are updated in descending order so the stage state is overwritten in place.  The
+// single_resident.cu.  The
 // upstream neighbour of a thread's first cell is the previous thread's last cell: every thread posts that cell
 // (n doubles) to a double-buffered shared array xch[parity][species][thread + 1], slot 0 holding the inlet, and
 // reads slot `thread` after the ONE __syncthreads of the stage: n stores + n loads, conflict-free, no lane
@@ -261,38 +261,52 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
         for (int s = 0; s < N; ++s) upx[s] = post[s * 33 + warp];
       }
 #endif
+      // All M cells are solved before any is updated: their chains are independent and interleave (one vote for
+      // the rare dense-LU redo instead of one per cell), and the update needs no ordering.
+      double k[M][N];
+      bool redo[M];
+      bool any_redo = false;
 #pragma unroll
-      for (int j = M - 1; j >= 0; --j) {
-        double k[N], upv[N];
+      for (int j = 0; j < M; ++j) {
+        double upv[N];
 #pragma unroll
         for (int s = 0; s < N; ++s) upv[s] = (j > 0) ? src[j - 1][s] : upx[s];
-        const bool redo = scan_row<N>(sc, colc[0], colc[1], src[j], upv, k);
-        if (__any_sync(0xffffffffu, redo)) {
+        redo[j] = scan_row<N>(sc, colc[0], colc[1], src[j], upv, k[j]);
+        any_redo |= redo[j];
+      }
+      if (__any_sync(0xffffffffu, any_redo)) {
+#pragma unroll
+        for (int j = 0; j < M; ++j) {
+          if (!__any_sync(0xffffffffu, redo[j])) continue;
           VecN<N> cc, uu;
 #pragma unroll
           for (int s = 0; s < N; ++s) {
             cc.v[s] = src[j][s];
-            uu.v[s] = upv[s];
+            uu.v[s] = (j > 0) ? src[j - 1][s] : upx[s];
           }
           const VecN<N> kk = cold_row<N>(sc, fe, 1.0, cc, uu);  // unscaled like scan_row
 #pragma unroll
-          for (int s = 0; s < N; ++s) k[s] = kk.v[s];
+          for (int s = 0; s < N; ++s) k[j][s] = kk.v[s];
         }
+      }
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
 #pragma unroll
         for (int s = 0; s < N; ++s) {
+          const double kv = k[j][s];
           if (which == 0) {
-            y[j][s] = fma(k[s], cdt, y[j][s]);
+            y[j][s] = fma(kv, cdt, y[j][s]);
           } else if (which == 1) {
-            if (ACC_SH) my_acc[j * N + s] = k[s];
-            else acc[j][s] = k[s];
-            u[j][s] = fma(k[s], ch2, y[j][s]);
+            if (ACC_SH) my_acc[j * N + s] = kv;
+            else acc[j][s] = kv;
+            u[j][s] = fma(kv, ch2, y[j][s]);
           } else if (which == 2 || which == 3) {
-            if (ACC_SH) my_acc[j * N + s] = fma(k[s], 2.0, my_acc[j * N + s]);
-            else acc[j][s] = fma(k[s], 2.0, acc[j][s]);
-            u[j][s] = fma(k[s], which == 2 ? ch2 : cdt, y[j][s]);
+            if (ACC_SH) my_acc[j * N + s] = fma(kv, 2.0, my_acc[j * N + s]);
+            else acc[j][s] = fma(kv, 2.0, acc[j][s]);
+            u[j][s] = fma(kv, which == 2 ? ch2 : cdt, y[j][s]);
           } else {
             const double a = ACC_SH ? my_acc[j * N + s] : acc[j][s];
-            y[j][s] = fma(a + k[s], ch6, y[j][s]);
+            y[j][s] = fma(a + kv, ch6, y[j][s]);
           }
         }
       }
