@@ -277,13 +277,17 @@ kern_t pick(int method, int arith) {
 }
 
 const int kM[] = {2, 4, 5, 6, 7, 8, 10, 12, 13, 14, 16, 17, 20, 25, 28, 32};
-const int kMmw[] = {8, 16, 32};
+const int kMmw[] = {8, 12, 16, 20, 24, 28, 32};
 
 kern_t lookup(int M, bool mw, int method, int arith) {
   if (mw) {
     switch (M) {
       case 8: return pick<8, true>(method, arith);
+      case 12: return pick<12, true>(method, arith);
       case 16: return pick<16, true>(method, arith);
+      case 20: return pick<20, true>(method, arith);
+      case 24: return pick<24, true>(method, arith);
+      case 28: return pick<28, true>(method, arith);
       case 32: return pick<32, true>(method, arith);
     }
     return nullptr;
@@ -321,13 +325,16 @@ bool single_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std:
     return false;
   }
   char buf[160];
+  const char* force = getenv("CHROM_FORCE_M");  // experiments only
+  const uint64_t fill_warps = (uint64_t)sm_count * 8u;
+
+  // ---- candidate 1: a single warp per column (nz <= 1024) ------------------------------------------------
+  // Maximise (fraction of lane-slots doing real cells) x (measured efficiency of the chunk size); when the
+  // batch cannot fill the machine prefer short chunks (more lanes in flight per column).
+  double sw_score = -1.0;
+  int swM = 0, swL = 0, swCpw = 0;
+  bool latency_bound = false;
   if (nz <= 32u * 32u) {
-    // single warp per column: maximise the fraction of lane-slots doing real cells; when the batch
-    // cannot fill the machine prefer short chunks (more lanes in flight per column).
-    const uint64_t fill_warps = (uint64_t)sm_count * 8u;
-    double best_score = -1.0;
-    int bestM = 0, bestL = 0, bestCpw = 0;
-    const char* force = getenv("CHROM_FORCE_M");  // experiments only
     for (int M : kM) {
       if (force && atoi(force) != M) continue;
       const int L = (int)((nz + M - 1) / M);
@@ -335,59 +342,83 @@ bool single_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std:
       const int cpw = 32 / L;
       const double eff = (double)nz * cpw / (32.0 * M);
       const uint64_t warps = (b.n_cols + cpw - 1) / cpw;
-      // shuffle + control overhead is amortised over M cells: ~2% per 1/M
-      double score = eff * (1.0 - 0.25 / M);
-      if (warps < fill_warps) score = eff / M;  // latency-bound batch: shortest critical path wins
-      if (score > best_score) {
-        best_score = score;
-        bestM = M;
-        bestL = L;
-        bestCpw = cpw;
+      // measured fraction of FP64 peak at a perfect fit (32 lanes per column, gpurun_out/single_shapes_*.jsonl):
+      // flat 0.69-0.72 for 6 <= M <= 25, lower for very short chunks (per-lane overhead) and for M >= 28
+      // (255 registers: 8 warps per SM)
+      const double eff_m = M < 6 ? 0.645 : (M == 12 || M == 25) ? 0.72 : M <= 25 ? 0.70 : M == 28 ? 0.675 : 0.65;
+      double score = eff * eff_m;
+      if (warps < fill_warps) {  // latency-bound batch: shortest critical path wins
+        score = eff / M;
+        latency_bound = true;
+      }
+      if (score > sw_score) {
+        sw_score = score;
+        swM = M;
+        swL = L;
+        swCpw = cpw;
       }
     }
-    if (bestM == 0) return false;
-    const uint64_t warps = ((uint64_t)b.n_cols + bestCpw - 1) / bestCpw;
+  }
+
+  // ---- candidate 2: several warps per column, one CTA per column (nz > 512) ------------------------------
+  // score = (fraction of lane-slots doing real cells) x (measured efficiency of the chunk size at a perfect fit)
+  // x (balance of the resident warps over the 4 SM sub-partitions: 6 warps per SM run at 6/8).
+  double mw_score = -1.0;
+  int mwM = 0, mwW = 0;
+  if (nz > 512u && !(latency_bound && swM)) {
+    for (int M : kMmw) {
+      if (force && atoi(force) != M) continue;
+      const int W = (int)((nz + 32u * M - 1) / (32u * M));
+      if (W * 32 > mw_max_threads(M)) continue;
+      const double eff_m = M <= 8 ? 0.55 : M <= 12 ? 0.647 : M <= 16 ? 0.691 : M <= 20 ? 0.695 : M <= 24 ? 0.711 : 0.65;
+      int ctas = 1;
+      if (kern_t k = lookup(M, true, b.method, b.arith)) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, (const void*)k, W * 32, 0) != cudaSuccess || ctas < 1) {
+          cudaGetLastError();
+          ctas = 1;
+        }
+      }
+      const int wt = W * ctas;
+      const double balance = (double)wt / (4.0 * ((wt + 3) / 4));
+      const double score = (double)nz / ((double)W * 32.0 * M) * eff_m * balance;
+      if (score >= mw_score) {
+        mw_score = score;
+        mwM = M;
+        mwW = W;
+      }
+    }
+  }
+
+  if (swM && (sw_score >= mw_score || !mwM)) {
+    const uint64_t warps = ((uint64_t)b.n_cols + swCpw - 1) / swCpw;
     g->kind = 1;
-    g->M = bestM;
-    g->L = bestL;
-    g->cpw = bestCpw;
+    g->M = swM;
+    g->L = swL;
+    g->cpw = swCpw;
     g->warps_per_col = 1;
     g->block = dim3(kBlockThreads);
     g->grid = dim3((unsigned)((warps + (kBlockThreads / 32) - 1) / (kBlockThreads / 32)));
     g->smem = 0;
-    g->cols_per_wave = (uint32_t)(sm_count * min_blocks_for(bestM) * (kBlockThreads / 32) * bestCpw);
+    g->cols_per_wave = (uint32_t)(sm_count * min_blocks_for(swM) * (kBlockThreads / 32) * swCpw);
     snprintf(buf, sizeof buf, "single_resident<M=%d,%s,%s> lanes/col=%d cols/warp=%d grid=%u block=%d",
-             bestM, b.method == CHROM_RK4 ? "RK4" : "Euler", arith_name(b.arith),
-             bestL, bestCpw, g->grid.x, kBlockThreads);
+             swM, b.method == CHROM_RK4 ? "RK4" : "Euler", arith_name(b.arith),
+             swL, swCpw, g->grid.x, kBlockThreads);
     g->name = buf;
     return true;
   }
-  // multi-warp per column: one CTA per column, fewest padded cells, then the largest chunk
-  int bestM = 0, bestW = 0;
-  uint32_t best_pad = 0xffffffffu;
-  for (int M : kMmw) {
-    const int W = (int)((nz + 32u * M - 1) / (32u * M));
-    if (W * 32 > mw_max_threads(M)) continue;
-    const uint32_t pad = (uint32_t)W * 32u * M - nz;
-    if (pad <= best_pad) {
-      best_pad = pad;
-      bestM = M;
-      bestW = W;
-    }
-  }
-  if (bestM == 0) return false;
+  if (mwM == 0) return false;
   g->kind = 2;
-  g->M = bestM;
-  g->L = bestW * 32;
+  g->M = mwM;
+  g->L = mwW * 32;
   g->cpw = 1;
-  g->warps_per_col = bestW;
-  g->block = dim3(bestW * 32);
+  g->warps_per_col = mwW;
+  g->block = dim3(mwW * 32);
   g->grid = dim3(b.n_cols);
   g->smem = 0;
-  g->cols_per_wave = (uint32_t)(sm_count * std::max(1, 512 / (bestW * 32)));
-  snprintf(buf, sizeof buf, "single_resident_mw<M=%d,%s,%s> warps/col=%d grid=%u block=%d", bestM,
-           b.method == CHROM_RK4 ? "RK4" : "Euler", arith_name(b.arith), bestW,
-           g->grid.x, bestW * 32);
+  g->cols_per_wave = (uint32_t)(sm_count * std::max(1, 512 / (mwW * 32)));
+  snprintf(buf, sizeof buf, "single_resident_mw<M=%d,%s,%s> warps/col=%d grid=%u block=%d", mwM,
+           b.method == CHROM_RK4 ? "RK4" : "Euler", arith_name(b.arith), mwW,
+           g->grid.x, mwW * 32);
   g->name = buf;
   return true;
 }
