@@ -31,6 +31,7 @@ struct DeviceState {
   int id = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;      // second compute stream: consecutive chunks of a one-shot solve overlap
   cudaStream_t copy_stream = nullptr;  // device->host copies overlapped with compute (one-shot solves)
   void* flush_buf = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // h2d0 h2d1 k0 k1 d2h0 d2h1
@@ -462,6 +463,7 @@ int32_t chrom_cuda_create(const int32_t* device_ids, int32_t n_devices, chrom_cu
                          id, prop.name, prop.major, prop.minor));
     d.sm_count = prop.multiProcessorCount;
     CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+    CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&d.stream2, cudaStreamNonBlocking));
     CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
     {
       cudaMemPool_t pool;
@@ -483,6 +485,7 @@ void chrom_cuda_destroy(chrom_cuda_ctx* ctx) {
     for (auto& ev : d.ev)
       if (ev) cudaEventDestroy(ev);
     if (d.stream) cudaStreamDestroy(d.stream);
+    if (d.stream2) cudaStreamDestroy(d.stream2);
     if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
     if (d.flush_buf) cudaFree(d.flush_buf);
   }
@@ -764,7 +767,9 @@ static int32_t solve_pipelined(chrom_cuda_ctx* ctx, chrom_cuda_plan* plan, doubl
     CUDA_TRY(ctx, cudaSetDevice(d.id));
     CUDA_TRY(ctx, cudaMemsetAsync(sh.status.p, 0, sh.n_cols * sizeof(long long), d.stream));
     CUDA_TRY(ctx, cudaEventRecord(d.ev[2], d.stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(d.stream2, d.ev[2], 0));  // the status memset precedes every chunk
   }
+  std::vector<uint64_t> chunk_idx(plan->shards.size(), 0);
   bool more = true;
   while (more && rc == CHROM_OK) {
     more = false;
@@ -778,14 +783,18 @@ static int32_t solve_pipelined(chrom_cuda_ctx* ctx, chrom_cuda_plan* plan, doubl
       const uint64_t c0 = next[si], cnt = std::min<uint64_t>(chunk, sh.n_cols - c0);
       next[si] = c0 + cnt;
       more |= next[si] < sh.n_cols;
+      // Consecutive chunks alternate between two compute streams: a kernel boundary in ONE stream is a full
+      // barrier (the next wave cannot start until the last block of this one has ended); across two streams the
+      // blocks of chunk i+1 fill the SMs as those of chunk i drain.
+      cudaStream_t cs = (chunk_idx[si]++ & 1u) ? d.stream2 : d.stream;
       const BatchDev b = sub_batch(plan, sh, c0, cnt);
-      rc = launch_batch(ctx, b, sh.g, d.stream);
+      rc = launch_batch(ctx, b, sh.g, cs);
       if (rc != CHROM_OK) break;
       launches += sh.g.launches_per_execute;
       cudaEvent_t ev;
       CUDA_TRY(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
       events[si].push_back(ev);
-      CUDA_TRY(ctx, cudaEventRecord(ev, d.stream));
+      CUDA_TRY(ctx, cudaEventRecord(ev, cs));
       CUDA_TRY(ctx, cudaStreamWaitEvent(d.copy_stream, ev, 0));
       auto copy = [&](void* host, const void* dev, size_t per_col_bytes) -> cudaError_t {
         if (!host || !dev) return cudaSuccess;
@@ -805,9 +814,12 @@ static int32_t solve_pipelined(chrom_cuda_ctx* ctx, chrom_cuda_plan* plan, doubl
     Shard& sh = *plan->shards[si];
     DeviceState& d = ctx->devs[sh.dev];
     cudaSetDevice(d.id);
+    // the kernel interval ends when the last chunk of EITHER compute stream has finished
+    for (size_t k = events[si].size(); k > 0 && k + 2 > events[si].size(); --k) cudaStreamWaitEvent(d.stream, events[si][k - 1], 0);
     cudaEventRecord(d.ev[3], d.stream);
     cudaError_t e = cudaStreamSynchronize(d.copy_stream);
     if (e == cudaSuccess) e = cudaEventSynchronize(d.ev[3]);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream2);
     if (e == cudaSuccess) cudaEventElapsedTime(&sh.kernel_ms, d.ev[2], d.ev[3]);
     kmax = std::max(kmax, sh.kernel_ms);
     for (cudaEvent_t ev : events[si]) cudaEventDestroy(ev);
