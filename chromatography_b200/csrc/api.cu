@@ -241,6 +241,8 @@ int32_t build_shard(chrom_cuda_plan* plan, Shard& sh, const chrom_single_col* sc
   b.nz = cfg.n_points;
   b.n_species = cfg.n_species;
   b.steps = (uint32_t)cfg.time_steps;
+  b.step_begin = 0;
+  b.step_end = b.steps;
   b.stages = stages;
   b.outlet_stride = sh.outlet.p ? (uint32_t)cfg.outlet_stride : 0u;
   b.snapshot_stride = sh.snapshots.p ? (uint32_t)cfg.snapshot_stride : 0u;
@@ -788,6 +790,49 @@ static int32_t solve_pipelined(chrom_cuda_ctx* ctx, chrom_cuda_plan* plan, doubl
       // blocks of chunk i+1 fill the SMs as those of chunk i drain.
       cudaStream_t cs = (chunk_idx[si]++ & 1u) ? d.stream2 : d.stream;
       const BatchDev b = sub_batch(plan, sh, c0, cnt);
+      // The copy of the LAST chunk is the one nothing overlaps.  Where the kernel can continue from a carried
+      // state (register-resident single-species kernels, no on-device summary, no snapshots), that chunk is
+      // advanced in kSlices time slices and the outlet samples of a slice go back while the next one computes.
+      constexpr uint32_t kSlices = 4;
+      const bool last_chunk = next[si] >= sh.n_cols;
+      if (last_chunk && (sh.g.kind == 1 || sh.g.kind == 2) && !summary && !snapshots && outlet && b.outlet &&
+          b.final_state && b.outlet_stride > 0 && b.steps >= 64u * kSlices) {
+        const size_t n_out = plan->n_out;
+        for (uint32_t k = 0; k < kSlices && rc == CHROM_OK; ++k) {
+          BatchDev bs = b;
+          bs.step_begin = (uint32_t)((uint64_t)b.steps * k / kSlices);
+          bs.step_end = (uint32_t)((uint64_t)b.steps * (k + 1) / kSlices);
+          if (k > 0) bs.y0 = b.final_state;  // every slice leaves its state there
+          rc = launch_batch(ctx, bs, sh.g, cs);
+          if (rc != CHROM_OK) break;
+          launches += sh.g.launches_per_execute;
+          cudaEvent_t evs;
+          CUDA_TRY(ctx, cudaEventCreateWithFlags(&evs, cudaEventDisableTiming));
+          events[si].push_back(evs);
+          CUDA_TRY(ctx, cudaEventRecord(evs, cs));
+          CUDA_TRY(ctx, cudaStreamWaitEvent(d.copy_stream, evs, 0));
+          const size_t slot_a = k == 0 ? 0 : bs.step_begin / b.outlet_stride + 1;  // slot 0 = the initial state
+          const size_t slot_b = bs.step_end / b.outlet_stride + 1;
+          if (slot_b > slot_a) {
+            CUDA_TRY(ctx, cudaMemcpy2DAsync(outlet + (sh.col0 + c0) * n_out + slot_a, n_out * sizeof(double),
+                                            b.outlet + slot_a, n_out * sizeof(double), (slot_b - slot_a) * sizeof(double),
+                                            cnt, cudaMemcpyDeviceToHost, d.copy_stream));
+            bytes += cnt * (slot_b - slot_a) * sizeof(double);
+          }
+        }
+        if (rc != CHROM_OK) break;
+        if (final_state) {
+          CUDA_TRY(ctx, cudaMemcpyAsync(final_state + (sh.col0 + c0) * sl, b.final_state, cnt * sl * sizeof(double),
+                                        cudaMemcpyDeviceToHost, d.copy_stream));
+          bytes += cnt * sl * sizeof(double);
+        }
+        if (status) {
+          CUDA_TRY(ctx, cudaMemcpyAsync(status + sh.col0 + c0, b.status, cnt * sizeof(long long), cudaMemcpyDeviceToHost,
+                                        d.copy_stream));
+          bytes += cnt * sizeof(long long);
+        }
+        continue;
+      }
       rc = launch_batch(ctx, b, sh.g, cs);
       if (rc != CHROM_OK) break;
       launches += sh.g.launches_per_execute;
@@ -815,7 +860,7 @@ static int32_t solve_pipelined(chrom_cuda_ctx* ctx, chrom_cuda_plan* plan, doubl
     DeviceState& d = ctx->devs[sh.dev];
     cudaSetDevice(d.id);
     // the kernel interval ends when the last chunk of EITHER compute stream has finished
-    for (size_t k = events[si].size(); k > 0 && k + 2 > events[si].size(); --k) cudaStreamWaitEvent(d.stream, events[si][k - 1], 0);
+    for (size_t k = events[si].size(); k > 0 && k + 6 > events[si].size(); --k) cudaStreamWaitEvent(d.stream, events[si][k - 1], 0);
     cudaEventRecord(d.ev[3], d.stream);
     cudaError_t e = cudaStreamSynchronize(d.copy_stream);
     if (e == cudaSuccess) e = cudaEventSynchronize(d.ev[3]);

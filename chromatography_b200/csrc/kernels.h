@@ -37,6 +37,8 @@ struct BatchDev {
   uint32_t nz;
   uint32_t n_species;
   uint32_t steps;
+  uint32_t step_begin, step_end;  // the launch advances steps [step_begin, step_end) (register-resident single-species
+                                  // kernels only: a one-shot solve time-slices its last chunk; y0 = the carried state)
   uint32_t stages;  // table entries per step
   uint32_t outlet_stride, snapshot_stride;
   uint32_t n_out, n_snap;

@@ -100,9 +100,13 @@ __global__ void __launch_bounds__(MW ? mw_max_threads(M) : kBlockThreads, MW ? 1
       if (j < nv) dst[cell0 + j] = y[j];
   };
 
+  // This launch advances steps [s0, s1); s0 > 0 continues a solve from the carried state in y0 (the last chunk
+  // of a one-shot solve is time-sliced so that its outlet series can go back to the host slice by slice; the
+  // host never slices a solve that accumulates the on-device summary).
+  const uint32_t s0 = b.step_begin, s1 = b.step_end;
   // step 0 samples (initial condition: rk4.rs:254-255)
   double v_prev = 0.0, s_area = 0.0, s_mom = 0.0, s_max = 0.0, s_tmax = 0.0;
-  {
+  if (s0 == 0) {
     const double v0 = outlet_value();
     v_prev = v0;
     s_max = v0;
@@ -112,12 +116,23 @@ __global__ void __launch_bounds__(MW ? mw_max_threads(M) : kBlockThreads, MW ? 1
   uint32_t out_count = b.outlet_stride, snap_count = b.snapshot_stride;
   uint32_t out_slot = 1, snap_slot = 1;
   bool done = false;
+  if (s0 > 0) {
+    if (b.outlet_stride) {
+      out_slot = s0 / b.outlet_stride + 1;
+      out_count = b.outlet_stride - s0 % b.outlet_stride;
+    }
+    if (b.snapshot_stride) {
+      snap_slot = s0 / b.snapshot_stride + 1;
+      snap_count = b.snapshot_stride - s0 % b.snapshot_stride;
+    }
+    done = (b.status != nullptr) && (b.status[colc] != 0);  // validate_state already fired in an earlier slice
+  }
 
   double n0 = 0.0, n1 = 0.0, n2 = 0.0;
-  n0 = tab[0];
+  n0 = tab[(size_t)s0 * ST];
   if (ST == 3) {
-    n1 = tab[1];
-    n2 = tab[2];
+    n1 = tab[(size_t)s0 * ST + 1];
+    n2 = tab[(size_t)s0 * ST + 2];
   }
 
   // upwind value for the first cell of this lane at the current stage
@@ -131,7 +146,7 @@ __global__ void __launch_bounds__(MW ? mw_max_threads(M) : kBlockThreads, MW ? 1
     return (p == 0) ? inlet : up;
   };
 
-  for (uint32_t step = 0; step < steps; ++step) {
+  for (uint32_t step = s0; step < s1; ++step) {
     const double cin0 = n0, cin1 = n1, cin2 = n2;
     if (step + 1 < steps) {  // prefetch the next step's inlet values
       const double* nx = tab + (size_t)(step + 1) * ST;

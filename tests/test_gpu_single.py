@@ -291,3 +291,41 @@ def test_solve_scan_cfl_sweep(ctx):
     assert 0 < n_err < len(out)  # the scan crosses the stability limit
     with pytest.raises(cb.SolverError, match="one SolverConfiguration per scenario"):
         solver.solve_scan(scenarios, configs[:-1])
+
+
+@pytest.mark.parametrize("method", ["rk4", "euler"])
+@pytest.mark.parametrize("stride", [1, 3])
+def test_time_sliced_last_chunk(ctx, method, stride):
+    """One-shot solves without an on-device summary advance their LAST chunk of columns in time slices (state
+    carried through final_state) so that its outlet series goes back slice by slice.  Same bits as the single
+    launch of the plan path, including the slot arithmetic of a non-unit outlet stride and a validate_state
+    failure that happens in an early slice of a column of the last chunk (later slices must not overwrite it)."""
+    gm, om = METHODS[method]
+    n_cols, T, steps = (20_000 if stride == 1 else 48_000), 30.0, 500  # >= 64 MB of outputs: the chunked pipeline
+    a = W.tfa_sweep_arrays(n_cols, seed=11)
+    from chromatography_b200 import _ffi
+    cols = (_ffi.SingleCol * n_cols)()
+    arr = np.frombuffer(cols, dtype=np.float64).reshape(n_cols, 7)
+    for j, k in enumerate(["lambda_", "langmuir_k", "port_number", "fe", "ue", "dz"]):
+        arr[:, j] = a[k]
+    arr[:, 6] = 0.0
+    arr[n_cols - 2, 4] *= 400.0  # CFL >> 1 in a column of the last chunk: non-finite before the last slice
+    tables = cb.tabulate_injection(cb.TemporalInjection.gaussian(10.0, 3.0, 0.1), gm, T, steps)[None]
+    cfg = cb.make_cfg(gm, T, steps, 100, 1, stride, 0, cb.ARITH_EXACT)
+    one = cb.solve_single_batch(ctx, cfg, cols, tables)
+    plan = cb.Plan(ctx, cfg, cols, tables, want=cb.WANT_OUTLET | cb.WANT_FINAL | cb.WANT_STATUS)
+    plan.execute()
+    ref = plan.download()
+    plan.close()
+    assert one.timing["kernel_launches"] > ref.timing["kernel_launches"] + 3, "expected chunks and time slices"
+    assert ref.status[n_cols - 2] != 0 and abs(ref.status[n_cols - 2]) < steps - steps // 4  # before the last slice
+    np.testing.assert_array_equal(one.status, ref.status)
+    ok = ref.status == 0
+    assert ok.sum() == n_cols - 1
+    assert_bit_equal(one.outlet[ok], ref.outlet[ok], "outlet")
+    assert_bit_equal(one.final_state[ok], ref.final_state[ok], "final")
+    models = W.tfa_sweep_models(n_cols, seed=11)
+    pick = [n_cols - 1, n_cols - 3, n_cols - 4000]
+    oo, of, _ = O.solve_single_batch([to_oracle(models[i]) for i in pick], om, T, steps)
+    assert_bit_equal(one.outlet[pick], oo[:, ::stride], "outlet vs oracle")
+    assert_bit_equal(one.final_state[pick], of, "final vs oracle")
