@@ -410,61 +410,6 @@ __device__ __forceinline__ bool fast_row_spec(const SpeciesConst* sc, const doub
 // N > 0: compile-time n (registers); N == 0: runtime n (local arrays of kNMax).
 // ------------------------------------------------------------------------------------------------
 
-// Compile-time n: everything in registers, 4n doubles of state (K, p -> g*p, rhs -> x, suffix max ->
-// reciprocal pivot), two 128-bit shared loads of constants per species.  Reads the cell from shared
-// memory itself; the solution is left in x[].
-template <int N>
-__device__ __forceinline__ bool structured_cell(const SpeciesConst* sc, double cg, const double* SRC,
-                                                const double* inlet_row, uint32_t nz, uint32_t cc, double (&x)[N]) {
-  double K[N], pw[N], d[N];
-  double S = 0.0;
-#pragma unroll
-  for (int s = 0; s < N; ++s) {
-    const double c = SRC[(size_t)s * nz + cc];
-    const double up = (cc > 0) ? SRC[(size_t)s * nz + cc - 1] : inlet_row[s];
-    const double2 kf = *reinterpret_cast<const double2*>(&sc[s].K);  // {K, feNK}
-    K[s] = kf.x;
-    x[s] = (c - up) * cg;
-    S = fma(kf.x, c, S);
-    pw[s] = kf.y * c;  // feNK_s * c_s; p_s = pw_s / D^2
-  }
-  const double rD = fast_rcp(1.0 + S);
-  const double rD2 = rD * rD;
-  double sfx = 0.0;
-#pragma unroll
-  for (int s = N - 1; s >= 0; --s) {
-    d[s] = sfx * rD2;  // max_{r>s} |p_r|, parked until the forward sweep reaches s
-    sfx = fmax(sfx, fabs(pw[s]));
-  }
-  double g = 1.0, carry = 0.0;
-  bool redo = false;
-#pragma unroll
-  for (int i = 0; i < N; ++i) {
-    const double2 af = *reinterpret_cast<const double2*>(&sc[i].a0);  // {a0, feNK}
-    const double alpha = fma(af.y, rD, af.x);                        // 1 + fe*(lambda_i + nbar_i K_i / D)
-    const double p = pw[i] * rD2;
-    const double b_i = fma(p, carry, x[i]);
-    const double t = g * p;
-    const double piv = fma(-t, K[i], alpha);
-    const double gq = g * K[i];
-    redo |= (gq * d[i] > fabs(piv)) || (piv == 0.0);
-    const double rp = fast_rcp(piv);
-    pw[i] = t;
-    x[i] = b_i;
-    d[i] = rp;
-    carry = fma(gq * rp, b_i, carry);
-    g = g * (alpha * rp);
-  }
-  double Sx = 0.0;
-#pragma unroll
-  for (int i = N - 1; i >= 0; --i) {
-    const double xi = fma(pw[i], Sx, x[i]) * d[i];
-    x[i] = xi;
-    Sx = fma(K[i], xi, Sx);
-  }
-  return redo;
-}
-
 // The same elimination in closed form (compile-time n, registers).  Eliminating species 0..i-1 of
 // diag(alpha) - p q^T leaves the pivot alpha_i - p_i q_i / h_i with h_i = 1 - sum_{j<i} p_j q_j / alpha_j, and
 // the solution is x = z + v (q.z) / (1 - q.v), z = b / alpha, v = p / alpha: the n reciprocals are independent
@@ -890,11 +835,7 @@ __global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_reside
         const uint32_t cc = live ? cell : nz - 1;  // idle lanes recompute the last cell, never store
         double k[CAP];
         if constexpr (ARITH == CHROM_KARITH_STRUCT && N > 0) {
-#ifdef CHROM_STRUCT_SWEEP
-          const bool redo = structured_cell<N>(sc, cg, SRC, inlet + irow * n, nz, cc, k);
-#else
           const bool redo = scan_cell<N>(sc, cg, SRC, inlet + irow * n, nz, cc, k);
-#endif
           if (redo) redo_mask |= 1u << ci;
           else if (live) bad |= apply_stage<N, false>(st, cc, k, n);
         } else {

@@ -21,13 +21,6 @@
 #pragma once
 #include "multi_kernels.cuh"
 
-#ifndef CHROM_REG_XCH_SMEM
-#define CHROM_REG_XCH_SMEM 1  // 1: every thread posts its last cell to shared memory (C5 658 ms); 0: shuffle + warp-boundary slots (693 ms)
-#endif
-#ifndef CHROM_REG_DELAY_CONST
-#define CHROM_REG_DELAY_CONST 0  // 1: fence the second sweep's constant loads behind rD (no fewer spills, measured)
-#endif
-
 namespace chrom {
 namespace {
 
@@ -69,17 +62,11 @@ __device__ __forceinline__ bool scan_row(const SpeciesConst* sc, double kmax, do
   const bool nonneg = pmax_hi < 0x7ff00000u;
   const double pmax2 = __hiloint2double((int)(pmax_hi + 1u), 0) * rD2;
   double qv0 = 0.0, qv1 = 0.0, qz0 = 0.0, qz1 = 0.0;
-  // The second sweep's constants must not be fetched before rD exists: hoisted to the top of the stage they would
-  // hold 3n more registers across the first sweep and push y into local memory.
-  const SpeciesConst* sc2 = sc;
-#if CHROM_REG_DELAY_CONST
-  asm volatile("" : "+l"(sc2) : "d"(rD));
-#endif
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const double2 af = *reinterpret_cast<const double2*>(&sc2[i].a0);  // {a0, feNK}
+    const double2 af = *reinterpret_cast<const double2*>(&sc[i].a0);  // {a0, feNK}
     const double ra = fast_rcp(fma(af.y, rD, af.x));                    // 1 / alpha_i
-    const double Ki = sc2[i].K;
+    const double Ki = sc[i].K;
     x[i] *= ra;                   // z_i
     pv[i] = (pv[i] * rD2) * ra;   // v_i
     if (i & 1) {
@@ -236,7 +223,6 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
     // (0 Euler; 1..4 RK4).  src/dst are register arrays; stages 2-4 run in place on u.
     auto stage = [&](double (&src)[M][N], int irow, int spar, int par, int which) {
       double upx[N];
-#if CHROM_REG_XCH_SMEM
       double* const post = xch + ((size_t)par * (T + 1) + tid) * XS;  // row of slot `tid`; the thread's own row is next
 #pragma unroll
       for (int s = 0; s < N; ++s) post[XS + s] = src[M - 1][s];
@@ -244,23 +230,6 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
       __syncthreads();
 #pragma unroll
       for (int s = 0; s < N; ++s) upx[s] = post[s];
-#else
-      // previous lane by shuffle; warp boundaries through xch[par][species][warp + 1], slot 0 = the inlet
-      double* const post = xch + (size_t)par * N * 33;  // [species][33]
-      const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-      for (int s = 0; s < N; ++s) {
-        const double last = src[M - 1][s];
-        upx[s] = __shfl_up_sync(0xffffffffu, last, 1);
-        if (lane == 31) post[s * 33 + warp + 1] = last;
-      }
-      if (tid < N) post[tid * 33] = inlet[spar][irow][tid];
-      __syncthreads();
-      if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < N; ++s) upx[s] = post[s * 33 + warp];
-      }
-#endif
       // All M cells are solved before any is updated: their chains are independent and interleave (one vote for
       // the rare dense-LU redo instead of one per cell), and the update needs no ordering.
       double k[M][N];

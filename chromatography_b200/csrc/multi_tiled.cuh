@@ -547,11 +547,7 @@ __global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi
           const bool owned = live && cc >= first_valid;
           double k[CAP];
           if constexpr (ARITH == CHROM_KARITH_STRUCT && N > 0) {
-#ifdef CHROM_STRUCT_SWEEP
-            const bool redo = structured_cell<(N > 0 ? N : 1)>(sc, cg, SRC, inlet_row, pitch, cc, k);
-#else
             const bool redo = scan_cell<(N > 0 ? N : 1)>(sc, cg, SRC, inlet_row, pitch, cc, k);
-#endif
             if (redo) redo_mask |= 1u << ci;
             else if (live) bad |= apply_stage<N, false>(st, cc, k, n) && owned;
           } else {
