@@ -1,6 +1,6 @@
 // single_stream.cu — LangmuirSingle columns too long for the register-resident path (nz > 8192,
 // e.g. the nz = 2^22 spatial-convergence column of BASELINE config 4): the state streams through
-// HBM/L2, FUSE time steps per pass (temporal blocking), all four RK4 stages of each step fused.
+// HBM/L2, FUSE time steps per pass (temporal blocking, RK4 and Euler), all four RK4 stages of each step fused.
 //
 // Replaces per launch FUSE iterations of the time loop (rk4.rs:266-332 / euler.rs:227-269) with
 // LangmuirSingle::compute_physics (langmuir_single.rs:445-516) evaluated 4 (or 1) times in registers.
@@ -44,7 +44,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32)
                          uint32_t out_slot0) {
   constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
   constexpr int kTile = 32 * kM;
-  constexpr int H = (METHOD == CHROM_RK4) ? 4 * FUSE : 0;  // RK4 stage values reach 4 cells upstream per step
+  // RK4 stage values reach 4 cells upstream per step, a forward-Euler step 1; an unfused Euler step needs no halo
+  // (the upstream neighbour of the tile's first cell is an input of the step)
+  constexpr int H = (METHOD == CHROM_RK4) ? 4 * FUSE : (FUSE > 1 ? FUSE : 0);
   constexpr int V = kTile - H;                             // cells a non-first tile contributes
   using Q = Coef<ARITH>;
   const int lane = threadIdx.x & 31;
@@ -84,8 +86,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32)
     for (int j = 0; j < kM; ++j) y[j] = (cell0 + j < (long long)nz) ? s[cell0 + j] : 0.0;
   }
   const bool inlet_lane = (tile == 0) && (lane == 0);
-  double euler_up = 0.0;  // Euler (never fused): the upstream neighbour of the tile's first cell is an input
-  if (METHOD == CHROM_EULER && lane == 0 && tile > 0) euler_up = s[cell0 - 1];
+  double euler_up = 0.0;  // unfused Euler: the upstream neighbour of the tile's first cell is an input
+  if (METHOD == CHROM_EULER && FUSE == 1 && lane == 0 && tile > 0) euler_up = s[cell0 - 1];
 
   auto exchange = [&](double last, double inlet) -> double {
     const double up = __shfl_up_sync(0xffffffffu, last, 1);
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32)
       }
     } else {
       double up = exchange(y[kM - 1], cin0);
-      if (lane == 0 && tile > 0) up = euler_up;
+      if (FUSE == 1 && lane == 0 && tile > 0) up = euler_up;
 #pragma unroll
       for (int j = kM - 1; j >= 0; --j) {
         const double k = q.rhs(y[j], j > 0 ? y[j - 1] : up);
@@ -260,13 +262,13 @@ skern_t pick_stream_f(int method, int arith) {
     if (arith == CHROM_ARITH_EXACT) return k_single_stream_step<CHROM_RK4, 1, FUSE, M>;
     return arith == CHROM_KARITH_POLY ? k_single_stream_step<CHROM_RK4, 2, FUSE, M> : k_single_stream_step<CHROM_RK4, 0, FUSE, M>;
   }
-  if (arith == CHROM_ARITH_EXACT) return k_single_stream_step<CHROM_EULER, 1, 1, M>;
-  return arith == CHROM_KARITH_POLY ? k_single_stream_step<CHROM_EULER, 2, 1, M> : k_single_stream_step<CHROM_EULER, 0, 1, M>;
+  if (arith == CHROM_ARITH_EXACT) return k_single_stream_step<CHROM_EULER, 1, FUSE, M>;
+  return arith == CHROM_KARITH_POLY ? k_single_stream_step<CHROM_EULER, 2, FUSE, M> : k_single_stream_step<CHROM_EULER, 0, FUSE, M>;
 }
 
 template <int M>
 skern_t pick_stream_m(int method, int arith, int fuse) {
-  if (method != CHROM_RK4 || fuse == 1) return pick_stream_f<1, M>(method, arith);
+  if (fuse == 1) return pick_stream_f<1, M>(method, arith);
   if (fuse == 2) return pick_stream_f<2, M>(method, arith);
   return fuse == 4 ? pick_stream_f<4, M>(method, arith) : pick_stream_f<8, M>(method, arith);
 }
@@ -278,7 +280,6 @@ skern_t pick_stream(int method, int arith, int fuse, int m) {
 // Steps fused per launch: snapshots are taken from the state between launches, so the snapshot
 // stride must be a multiple of the fusion depth.  CHROM_STREAM_FUSE overrides (experiments).
 int stream_fuse(const BatchDev& b) {
-  if (b.method != CHROM_RK4) return 1;
   int f = 8;
   if (const char* e = getenv("CHROM_STREAM_FUSE")) f = atoi(e) >= 8 ? 8 : (atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1));
   while (f > 1 && b.snapshots && b.snapshot_stride && (b.snapshot_stride % f) != 0) f /= 2;
@@ -307,7 +308,7 @@ bool single_stream_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::s
   (void)why;
   const int fuse = stream_fuse(b);
   const int kM = stream_m(), kWarps = stream_warps(), kTile = 32 * kM;
-  const int H = b.method == CHROM_RK4 ? 4 * fuse : 0;
+  const int H = b.method == CHROM_RK4 ? 4 * fuse : (fuse > 1 ? fuse : 0);
   const int V = kTile - H;
   const long long rest = (long long)b.nz - kTile;
   const int tiles = 1 + (rest > 0 ? (int)((rest + V - 1) / V) : 0);

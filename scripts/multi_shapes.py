@@ -25,14 +25,15 @@ def main():
         parts = spec.split(",")
         n, nz, cols, steps = (int(x) for x in parts[:4])
         env = dict(p.split("=") for p in parts[4:])
+        method = cb.EULER if env.pop("METHOD", "rk4") == "euler" else cb.RK4  # cell-stage updates: 1 per step for Euler
         arith = {"exact": cb.ARITH_EXACT, "fast": cb.ARITH_FAST}[env.pop("ARITH", "fast")]
         for k, v in env.items():
             os.environ[k] = v
         try:
             T = 600.0 * steps / 4096 * (512.0 / nz)  # the C5 time step scaled with dz: same CFL
             models = W.multi_batch_models(cols, n, nz)
-            cfg = cb.make_cfg(cb.RK4, T, steps, nz, n, 1, 0, arith)
-            c, sp, tab = cb.pack_multi(models, cb.RK4, T, steps)
+            cfg = cb.make_cfg(method, T, steps, nz, n, 1, 0, arith)
+            c, sp, tab = cb.pack_multi(models, method, T, steps)
             plan = cb.Plan(ctx, cfg, c, tab, species=sp, want=cb.WANT_OUTLET | cb.WANT_FINAL)
             desc = plan.describe()
             ms = []
@@ -42,7 +43,7 @@ def main():
             r = plan.download()
             plan.close()
             best = min(ms[1:])
-            units = cols * nz * steps * 4.0
+            units = cols * nz * steps * (4.0 if method == cb.RK4 else 1.0)
             print(json.dumps({"n": n, "nz": nz, "cols": cols, "steps": steps, "env": env, "kernel": desc,
                               "kernel_ms": best, "cell_stage_per_s": units / (best * 1e-3),
                               "tflops_alg": units * flops_per_cell_stage(n) / (best * 1e-3) / 1e12,
