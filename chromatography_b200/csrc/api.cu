@@ -289,6 +289,10 @@ int32_t build_shard(chrom_cuda_plan* plan, Shard& sh, const chrom_single_col* sc
     const char* no_reg = getenv("CHROM_MULTI_NO_REG");
     if (!forced && b.arith == CHROM_KARITH_STRUCT && !(no_reg && atoi(no_reg) != 0))
       ok = multi_reg_choose(b, d.sm_count, &sh.g, &why);
+    // Outside the register-resident kernel the 1x1 / 2x2 systems are cheapest as a dense register LU (measured on
+    // n = 2, nz = 8192: 1.63e11 vs 1.23e11 cell-stage/s for the closed-form elimination; the order flips at n >= 4).
+    if (!ok && b.arith == CHROM_KARITH_STRUCT && cfg.n_species <= 2 && cfg.arith != CHROM_ARITH_FAST_STRUCTURED)
+      b.arith = CHROM_ARITH_FAST;
     if (ok) {
       // no scratch, no streamed state
     } else if ((ok = !forced && multi_resident_choose(b, d.sm_count, &sh.g, &why))) {

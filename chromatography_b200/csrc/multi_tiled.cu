@@ -118,8 +118,18 @@ bool multi_tiled_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::str
     // fewest tiles at the widest tile, then the narrowest tile that still covers the column with them
     const uint32_t V = tw_max - halo;
     tiles = 1 + (b.nz - tw_max + V - 1) / V;
+    // A batch that cannot fill the machine is latency-bound: narrower tiles put more CTAs (warp per cell: fewer
+    // cells per warp and stage) on a column; a tile still owns at least max(8, 2 * halo) cells.
+    if (wj > 0 && (uint64_t)b.n_cols * tiles < (uint64_t)sm_count) {
+      const uint32_t own_min = std::max<uint32_t>(8u, 2u * halo);
+      const uint32_t by_machine = (uint32_t)sm_count / std::max<uint32_t>(1u, b.n_cols);
+      const uint32_t by_column = std::max<uint32_t>(1u, (b.nz > halo ? b.nz - halo : 1u) / own_min);
+      tiles = std::max(tiles, std::min(by_machine, by_column));
+    }
     tw = (b.nz + (tiles - 1) * halo + tiles - 1) / tiles;
     tw = std::min(std::max(tw, halo + 1), tw_max);
+    // the tile count that exactly covers the column at this width (its last tile owns at least one cell)
+    tiles = b.nz > tw ? 1 + (b.nz - tw + (tw - halo) - 1) / (tw - halo) : 1;
   }
   if (wj == 0) {  // threads: a multiple of 32 that keeps the cells per thread
     const uint32_t cpt = (tw + T - 1) / T;

@@ -374,6 +374,23 @@ __device__ __noinline__ void warp_cell_exact(int n, int lane, const SpeciesConst
   __syncwarp();  // the scratch matrices are reused by the warp's next cell
 }
 
+// Visits every (species, cell) pair of a tile's cells [j0, j1) with the whole CTA.  A wide tile (thread per cell)
+// walks species in the outer loop: coalesced, no index arithmetic.  A narrow tile (warp per cell: a few cells, up
+// to 256 species) would leave most of the CTA idle that way, so it runs over the flattened index instead.
+template <class F>
+__device__ __forceinline__ void for_tile(int n, uint32_t j0, uint32_t j1, int tid, int T, F f) {
+  const uint32_t w = j1 - j0;
+  if (w >= (uint32_t)T) {
+    for (int s = 0; s < n; ++s)
+      for (uint32_t j = j0 + tid; j < j1; j += T) f((uint32_t)s, j);
+  } else {
+    for (uint32_t i = tid; i < (uint32_t)n * w; i += T) {
+      const uint32_t s = i / w;
+      f(s, j0 + (i - s * w));
+    }
+  }
+}
+
 // ---- kernel -----------------------------------------------------------------------------------------------
 // threads per CTA of the warp-per-cell variants: 16 warps where the lane state is small (FAST, <= 2 species per lane)
 constexpr int tiled_warp_threads(int WJ, int ARITH) { return (ARITH != CHROM_ARITH_EXACT && WJ <= 2) ? 512 : 256; }
@@ -437,12 +454,11 @@ __global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi
       tabs[s] = b.tables + (size_t)sp.inj_table * b.steps * ST;
     }
     const double* gsrc = a.src + (size_t)col * n * nz + base;
-    for (int s = 0; s < n; ++s)
-      for (uint32_t j = tid; j < ncell; j += T) {
-        const double v = gsrc[(size_t)s * nz + j];
-        Y[(size_t)s * pitch + j] = v;
-        if (METHOD == CHROM_EULER) U0[(size_t)s * pitch + j] = v;
-      }
+    for_tile(n, 0u, ncell, tid, T, [&](uint32_t s, uint32_t j) {
+      const double v = gsrc[(size_t)s * nz + j];
+      Y[(size_t)s * pitch + j] = v;
+      if (METHOD == CHROM_EULER) U0[(size_t)s * pitch + j] = v;
+    });
     __syncthreads();
     if (owns_outlet)
       for (int s = tid; s < n; s += T) {
@@ -637,16 +653,15 @@ __global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi
       }
       if (b.snapshots && b.snapshot_stride && (done % b.snapshot_stride == 0u)) {
         double* gdst = b.snapshots + ((size_t)col * b.n_snap + done / b.snapshot_stride) * n * nz + base;
-        for (int s = 0; s < n; ++s)
-          for (uint32_t j = first_valid + tid; j < ncell; j += T) gdst[(size_t)s * nz + j] = Y[(size_t)s * pitch + j];
+        for_tile(n, first_valid, ncell, tid, T,
+                 [&](uint32_t s, uint32_t j) { gdst[(size_t)s * nz + j] = Y[(size_t)s * pitch + j]; });
       }
       if (any_bad && !flagged) {  // validate_state: the first bad step wins, NaN over Inf within it
         bool has_nan = false;
-        for (int s = 0; s < n; ++s)
-          for (uint32_t j = first_valid + tid; j < ncell; j += T) {
-            const double v = Y[(size_t)s * pitch + j];
-            has_nan |= (v != v);
-          }
+        for_tile(n, first_valid, ncell, tid, T, [&](uint32_t s, uint32_t j) {
+          const double v = Y[(size_t)s * pitch + j];
+          has_nan |= (v != v);
+        });
         const int any_nan = __syncthreads_or(has_nan);
         if (tid == 0) atomicMin(&a.code[col], (((unsigned long long)done) << 1) | (any_nan ? 0ull : 1ull));
         flagged = true;
@@ -654,8 +669,8 @@ __global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi
     }
     __syncthreads();
     double* gdst = a.dst + (size_t)col * n * nz + base;
-    for (int s = 0; s < n; ++s)
-      for (uint32_t j = first_valid + tid; j < ncell; j += T) gdst[(size_t)s * nz + j] = Y[(size_t)s * pitch + j];
+    for_tile(n, first_valid, ncell, tid, T,
+             [&](uint32_t s, uint32_t j) { gdst[(size_t)s * nz + j] = Y[(size_t)s * pitch + j]; });
     if (owns_outlet && b.summary)
       for (int s = tid; s < n; s += T) {
         double* g = a.gsumm + ((size_t)col * n + s) * 5;

@@ -26,7 +26,7 @@ def main():
         n, nz, cols, steps = (int(x) for x in parts[:4])
         env = dict(p.split("=") for p in parts[4:])
         method = cb.EULER if env.pop("METHOD", "rk4") == "euler" else cb.RK4  # cell-stage updates: 1 per step for Euler
-        arith = {"exact": cb.ARITH_EXACT, "fast": cb.ARITH_FAST}[env.pop("ARITH", "fast")]
+        arith = {"exact": cb.ARITH_EXACT, "fast": cb.ARITH_FAST, "dense": cb.ARITH_FAST_DENSE}[env.pop("ARITH", "fast")]
         for k, v in env.items():
             os.environ[k] = v
         try:
