@@ -107,7 +107,15 @@ bool multi_tiled_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::str
   } else {
     const uint32_t per_step = rk4 ? 4u : 1u;
     int fuse = env_int("CHROM_TILED_FUSE", 0);
-    if (fuse <= 0) fuse = (int)std::max<uint32_t>(1u, std::min<uint32_t>(8u, tw_max / (16u * per_step)));
+    if (fuse <= 0) {
+      // Steps per launch.  A batch that fills the machine amortises the tile's trip through HBM/L2 and the launch
+      // over as many steps as a halo of ~20 % of the tile allows (measured on n = 100, tile 52..56: 1 step 7.4e8,
+      // 2 steps 9.0e8, 3 steps 9.6e8 cell-stage/s); a batch that cannot fill it wants narrow tiles instead
+      // (more CTAs per column), i.e. a short halo.
+      const bool fills = (uint64_t)b.n_cols * ((b.nz + tw_max - 1) / tw_max) >= (uint64_t)sm_count;
+      fuse = (int)std::max<uint32_t>(1u, std::min<uint32_t>(8u, tw_max / (5u * per_step)));
+      if (!fills) fuse = std::min(fuse, (int)std::max<uint32_t>(1u, 4u / per_step));
+    }
     nsub = std::min<uint32_t>((uint32_t)fuse, b.steps);
     while (nsub > 1 && nsub * per_step * 2 > tw_max) --nsub;  // a tile must own at least half of its cells
     halo = nsub * per_step;
