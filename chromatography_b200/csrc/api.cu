@@ -296,11 +296,7 @@ int32_t build_shard(chrom_cuda_plan* plan, Shard& sh, const chrom_single_col* sc
     if (ok) {
       // no scratch, no streamed state
     } else if ((ok = !forced && multi_resident_choose(b, d.sm_count, &sh.g, &why))) {
-      const size_t per_thread = multi_scratch_per_thread((int)cfg.n_species, b.arith);
-      if (per_thread) {
-        CUDA_TRY(ctx, sh.scratch.alloc(per_thread * sh.g.grid.x * sh.g.block.x, d.stream));
-        b.scratch = sh.scratch.p;
-      }
+      // shared-memory-resident: no scratch, no streamed state
     } else if ((ok = multi_tiled_choose(b, d.sm_count, &sh.g, &why))) {
       // long columns / many species: the state streams through HBM/L2 in tiles (multi_tiled.cu)
       CUDA_TRY(ctx, sh.ping.alloc(sh.n_cols * state_len, d.stream));

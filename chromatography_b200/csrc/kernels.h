@@ -31,7 +31,7 @@ struct BatchDev {
   // streaming path scratch: two state buffers [n_cols][nz]
   double* ping;
   double* pong;
-  double* scratch;  // multi-species n > 8: per-thread dense-matrix scratch (see multi_scratch_per_thread)
+  double* scratch;  // multi-species warp-per-cell kernels: a dense-matrix block per warp (multi_tiled_scratch_doubles)
   // shape
   uint32_t n_cols;
   uint32_t nz;
@@ -87,7 +87,6 @@ size_t single_stream_extra_doubles();  // per column, behind the pong state buff
 bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why);
 cudaError_t multi_resident_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s);
 int multi_kernel_arith(int n_species, int arith);
-size_t multi_scratch_per_thread(int n_species, int kernel_arith);
 
 // multi_reg.cu — LangmuirMulti n <= 8 with the state in registers (FAST arithmetic)
 bool multi_reg_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why);

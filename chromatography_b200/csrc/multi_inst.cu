@@ -7,7 +7,7 @@
 #define CHROM_CAT(a, b) CHROM_CAT2(a, b)
 
 namespace chrom {
-typedef void (*mkern_t)(const BatchDev, double*);
+typedef void (*mkern_t)(const BatchDev);
 typedef void (*tkern_t)(const BatchDev, double*, const TiledArgs);
 mkern_t CHROM_CAT(multi_pick_, CHROM_MULTI_N)(int method, int arith) { return pick_n<CHROM_MULTI_N>(method, arith); }
 tkern_t CHROM_CAT(multi_tiled_pick_, CHROM_MULTI_N)(int method, int arith, int wj) {

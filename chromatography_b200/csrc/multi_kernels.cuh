@@ -29,8 +29,6 @@
 namespace chrom {
 namespace {
 
-constexpr int kNMax = 64;      // largest runtime n
-constexpr int kNMaxDecl = kNMax;
 
 struct alignas(16) SpeciesConst {  // per species, shared memory; {K, feNK} and {a0, feNK2} load as 128-bit pairs
   double K;      // langmuir_k
@@ -407,7 +405,6 @@ __device__ __forceinline__ bool fast_row_spec(const SpeciesConst* sc, const doub
 // g_i q_i max_{r>i} |p_r| > |d_i|; when it fires the caller redoes the cell with the dense
 // row-exchanging LU (register LU for n <= 8, scratch-memory LU beyond).  Same pivots, same factors,
 // O(n) registers: this is what makes n > 8 fit a thread and lets two warps more per SM fly.
-// N > 0: compile-time n (registers); N == 0: runtime n (local arrays of kNMax).
 // ------------------------------------------------------------------------------------------------
 
 // The same elimination in closed form (compile-time n, registers).  Eliminating species 0..i-1 of
@@ -480,212 +477,6 @@ __device__ __forceinline__ bool scan_cell(const SpeciesConst* sc, double cg, con
   return redo;
 }
 
-// Runtime n (9 .. kNMax): the same sweep over local arrays.
-template <int N>
-__device__ __forceinline__ bool structured_row(int n_rt, const SpeciesConst* sc, double cg, const double* c,
-                                               const double* up, double* k) {
-  constexpr int CAP = N > 0 ? N : kNMax;
-  const int n = N > 0 ? N : n_rt;
-  double S = 0.0;
-#pragma unroll
-  for (int s = 0; s < CAP; ++s)
-    if (s < n) S = fma(sc[s].K, c[s], S);
-  const double rD = fast_rcp(1.0 + S);
-  const double rD2 = rD * rD;
-  double p[CAP], d[CAP], gp[CAP], bb[CAP];  // p_i, reciprocal pivots, g_i*p_i, eliminated rhs
-  double pmax_suffix = 0.0;
-#pragma unroll
-  for (int s = CAP - 1; s >= 0; --s)
-    if (s < n) {
-      p[s] = sc[s].feNK * c[s] * rD2;
-      d[s] = pmax_suffix;  // max_{r>s} |p_r| parked here until the forward sweep reaches s
-      pmax_suffix = fmax(pmax_suffix, fabs(p[s]));
-    }
-  double g = 1.0, carry = 0.0;
-  bool need_pivot = false, singular = false;
-#pragma unroll
-  for (int i = 0; i < CAP; ++i)
-    if (i < n) {
-      const double q = sc[i].K;
-      const double alpha = fma(sc[i].feNK, rD, sc[i].a0);  // 1 + fe*(lambda_i + nbar_i K_i / D)
-      const double b_i = fma(p[i], carry, (c[i] - up[i]) * cg);
-      const double t = g * p[i];
-      const double piv = fma(-t, q, alpha);
-      const double gq = g * q;
-      need_pivot |= (gq * d[i] > fabs(piv));
-      singular |= (piv == 0.0);
-      const double rp = fast_rcp(piv);
-      gp[i] = t;
-      bb[i] = b_i;
-      d[i] = rp;
-      const double w = gq * rp;
-      carry = fma(w, b_i, carry);
-      g = g * (alpha * rp);
-    }
-  double Sx = 0.0;
-#pragma unroll
-  for (int i = CAP - 1; i >= 0; --i)
-    if (i < n) {
-      const double x = fma(gp[i], Sx, bb[i]) * d[i];
-      k[i] = x;
-      Sx = fma(sc[i].K, x, Sx);
-    }
-  return need_pivot || singular;
-}
-
-// Dense LU with partial pivoting for runtime n, matrix in per-thread scratch memory
-// (element e of this thread at a[e * stride]).  FAST arithmetic; only reached when the structured
-// sweep reports that a row exchange is needed (or an exactly singular pivot: identity fallback).
-__device__ void dense_row_scratch(int n, const SpeciesConst* sc, double cg, const double* c, const double* up,
-                                  double* k, double* a, size_t stride) {
-  auto A = [&](int i, int j) -> double& { return a[((size_t)i * n + j) * stride]; };
-  double S = 0.0;
-  for (int s = 0; s < n; ++s) S = fma(sc[s].K, c[s], S);
-  const double D = 1.0 + S, rD2 = 1.0 / (D * D);
-  for (int i = 0; i < n; ++i) {
-    const double p = sc[i].feNK * c[i] * rD2;
-    for (int j = 0; j < n; ++j) A(i, j) = -p * sc[j].K;
-    A(i, i) = fma(sc[i].feNK, D * rD2, sc[i].a0) + A(i, i);
-    k[i] = (c[i] - up[i]) * cg;
-  }
-  bool singular = false;
-  for (int i = 0; i < n; ++i) {
-    int piv = i;
-    double best = fabs(A(i, i));
-    for (int r = i + 1; r < n; ++r)
-      if (fabs(A(r, i)) > best) {
-        best = fabs(A(r, i));
-        piv = r;
-      }
-    if (piv != i) {
-      for (int q = i; q < n; ++q) {
-        const double t = A(i, q);
-        A(i, q) = A(piv, q);
-        A(piv, q) = t;
-      }
-      const double t = k[i];
-      k[i] = k[piv];
-      k[piv] = t;
-    }
-    singular |= (A(i, i) == 0.0);
-    const double rp = 1.0 / A(i, i);
-    for (int r = i + 1; r < n; ++r) {
-      const double l = A(r, i) * rp;
-      for (int q = i + 1; q < n; ++q) A(r, q) = fma(-l, A(i, q), A(r, q));
-      k[r] = fma(-l, k[i], k[r]);
-    }
-  }
-  for (int i = n - 1; i >= 0; --i) {
-    double s = k[i];
-    for (int q = i + 1; q < n; ++q) s = fma(-A(i, q), k[q], s);
-    k[i] = s / A(i, i);
-  }
-  if (singular)
-    for (int s = 0; s < n; ++s) k[s] = (c[s] - up[s]) * cg;
-}
-
-// EXACT for runtime n >= 5: compute_row with nalgebra's lu::try_invert_to and gemv, matrices in
-// per-thread scratch (mat, inverse, LU copy: 3 n^2 doubles).  Same operation order as exact_row<N>.
-__device__ void exact_row_scratch(int n, const SpeciesConst* sc, double fe, double ue, double dz, const double* c,
-                                  const double* up, double* k, double* scratch, size_t stride) {
-  const size_t nn = (size_t)n * n;
-  auto M = [&](int i, int j) -> double& { return scratch[((size_t)i + (size_t)j * n) * stride]; };             // mat
-  auto O = [&](int i, int j) -> double& { return scratch[(nn + (size_t)i + (size_t)j * n) * stride]; };        // inverse
-  auto A = [&](int i, int j) -> double& { return scratch[(2 * nn + (size_t)i + (size_t)j * n) * stride]; };    // LU copy
-  double sum_kc = 0.0;
-  for (int s = 0; s < n; ++s) sum_kc = x_add(sum_kc, x_mul(sc[s].K, c[s]));
-  const double denom = x_add(1.0, sum_kc);
-  const double denom2 = x_mul(denom, denom);
-  for (int i = 0; i < n; ++i) {
-    const double nb = sc[i].nbar, Ki = sc[i].K;
-    for (int j = 0; j < n; ++j) {
-      double J;
-      if (i == j) {
-        const double num = x_mul(x_mul(nb, Ki), x_sub(denom, x_mul(Ki, c[i])));
-        J = x_add(sc[i].lambda, x_div(num, denom2));
-      } else {
-        const double num = x_mul(x_mul(x_mul(-nb, Ki), sc[j].K), c[i]);
-        J = x_div(num, denom2);
-      }
-      M(i, j) = x_add((i == j) ? 1.0 : 0.0, x_mul(fe, J));
-    }
-  }
-  // lu::try_invert_to
-  bool ok = true;
-  for (int j = 0; j < n; ++j)
-    for (int i = 0; i < n; ++i) {
-      A(i, j) = M(i, j);
-      O(i, j) = (i == j) ? 1.0 : 0.0;
-    }
-  for (int i = 0; i < n && ok; ++i) {
-    int piv = i;
-    double the_max = fabs(A(i, i));
-    for (int r = i + 1; r < n; ++r) {
-      const double v = fabs(A(r, i));
-      if (v > the_max) {
-        the_max = v;
-        piv = r;
-      }
-    }
-    const double diag = A(piv, i);
-    if (diag == 0.0) {
-      ok = false;
-      break;
-    }
-    if (piv != i) {
-      for (int j = 0; j < n; ++j) {
-        const double t = O(i, j);
-        O(i, j) = O(piv, j);
-        O(piv, j) = t;
-      }
-      for (int j = 0; j <= i; ++j) {
-        const double t = A(i, j);
-        A(i, j) = A(piv, j);
-        A(piv, j) = t;
-      }
-    }
-    const double inv_diag = x_div(1.0, diag);
-    for (int r = i + 1; r < n; ++r) A(r, i) = x_mul(A(r, i), inv_diag);
-    for (int q = i + 1; q < n; ++q) {
-      if (piv != i) {
-        const double t = A(i, q);
-        A(i, q) = A(piv, q);
-        A(piv, q) = t;
-      }
-      const double neg_pivot = -A(i, q);
-      for (int r = i + 1; r < n; ++r) A(r, q) = x_add(x_mul(neg_pivot, A(r, i)), A(r, q));
-    }
-  }
-  if (ok) {
-    for (int cc = 0; cc < n; ++cc)
-      for (int i = 0; i + 1 < n; ++i) {
-        const double coeff = O(i, cc);
-        for (int r = i + 1; r < n; ++r) O(r, cc) = x_add(x_mul(-coeff, A(r, i)), O(r, cc));
-      }
-    for (int cc = 0; cc < n && ok; ++cc)
-      for (int i = n - 1; i >= 0; --i) {
-        const double diag = A(i, i);
-        if (diag == 0.0) {
-          ok = false;
-          break;
-        }
-        const double coeff = x_div(O(i, cc), diag);
-        O(i, cc) = coeff;
-        for (int r = 0; r < i; ++r) O(r, cc) = x_add(x_mul(-coeff, A(r, i)), O(r, cc));
-      }
-  }
-  if (!ok)  // identity fallback, langmuir_multi.rs:790-796
-    for (int j = 0; j < n; ++j)
-      for (int i = 0; i < n; ++i) O(i, j) = (i == j) ? 1.0 : 0.0;
-  // grad, gemv (column by column, j ascending), scale
-  for (int i = 0; i < n; ++i) k[i] = x_mul(O(i, 0), x_div(x_sub(c[0], up[0]), dz));
-  for (int j = 1; j < n; ++j) {
-    const double gj = x_div(x_sub(c[j], up[j]), dz);
-    for (int i = 0; i < n; ++i) k[i] = x_add(x_mul(O(i, j), gj), k[i]);
-  }
-  for (int s = 0; s < n; ++s) k[s] = x_mul(-ue, k[s]);
-}
-
 // Stage algebra of one cell (all species) on the shared-memory state.  Returns the non-finite flag of
 // the new state where the stage produces one.
 struct StageCtx {
@@ -698,9 +489,9 @@ struct StageCtx {
 };
 
 template <int N, bool EXACT>
-__device__ __forceinline__ bool apply_stage(const StageCtx& st, uint32_t cc, const double* k, int n_rt) {
-  constexpr int CAP = N > 0 ? N : kNMaxDecl;
-  const int n = N > 0 ? N : n_rt;
+__device__ __forceinline__ bool apply_stage(const StageCtx& st, uint32_t cc, const double* k, int /*n*/) {
+  constexpr int CAP = N;
+  constexpr int n = N;
   auto axpy = [](double y, double kk, double h) { return EXACT ? x_add(y, x_mul(kk, h)) : fma(kk, h, y); };
   bool bad = false;
 #pragma unroll
@@ -747,19 +538,20 @@ __device__ __noinline__ bool cold_cell(const SpeciesConst* sc, double fe, double
 }
 
 // ---- kernel ---------------------------------------------------------------------------------------
-// ARITH: CHROM_ARITH_FAST (dense register LU, N <= 8), CHROM_ARITH_EXACT, CHROM_KARITH_STRUCT.
-// N == 0: runtime n = b.n_species (9 .. kNMax); EXACT and STRUCT only.
+// ARITH: CHROM_ARITH_FAST (dense register LU), CHROM_ARITH_EXACT, CHROM_KARITH_STRUCT.  1 <= N <= 8 (larger
+// species counts run one warp per cell: multi_tiled.cuh).
 constexpr int multi_max_threads(int N, int ARITH) {
   return (ARITH == CHROM_KARITH_STRUCT && N > 0) ? 512 : ((N > 0 && N <= 2) ? 512 : 256);
 }
 
 template <int N, int METHOD, int ARITH>
-__global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_resident(const BatchDev b, double* scratch) {
+__global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_resident(const BatchDev b) {
+  static_assert(N >= 1 && N <= 8, "thread-per-cell kernels hold the n x n system in registers");
   constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
   constexpr bool EXACT = (ARITH == CHROM_ARITH_EXACT);
-  constexpr int CAP = N > 0 ? N : kNMax;
+  constexpr int CAP = N;
   extern __shared__ double smem[];
-  const int n = N > 0 ? N : (int)b.n_species;
+  constexpr int n = N;
   const uint32_t nz = b.nz;
   const int T = blockDim.x;
   const int tid = threadIdx.x;
@@ -772,9 +564,6 @@ __global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_reside
   double* summ = inlet + 3 * n;                      // [n][5]: area, moment, max, tmax, v_prev
   SpeciesConst* sc = (SpeciesConst*)(summ + 5 * n);  // [n]
   __shared__ const double* tabs[CAP];
-  // per-thread scratch (runtime-n dense paths): element e of this thread at my_scratch[e * sstride]
-  const size_t sstride = (size_t)gridDim.x * T;
-  double* my_scratch = scratch ? scratch + (size_t)blockIdx.x * T + tid : nullptr;
 
   const double dt = b.dt, h2 = b.half_dt, h6 = b.sixth_dt;
   const uint32_t steps = b.steps;
@@ -834,36 +623,31 @@ __global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_reside
         const bool live = cell < nz;
         const uint32_t cc = live ? cell : nz - 1;  // idle lanes recompute the last cell, never store
         double k[CAP];
-        if constexpr (ARITH == CHROM_KARITH_STRUCT && N > 0) {
+        if constexpr (ARITH == CHROM_KARITH_STRUCT) {
           const bool redo = scan_cell<N>(sc, cg, SRC, inlet + irow * n, nz, cc, k);
           if (redo) redo_mask |= 1u << ci;
           else if (live) bad |= apply_stage<N, false>(st, cc, k, n);
         } else {
           double c[CAP], up[CAP];
 #pragma unroll
-          for (int s = 0; s < CAP; ++s)
-            if (s < n) {
-              c[s] = SRC[(size_t)s * nz + cc];
-              up[s] = (cc > 0) ? SRC[(size_t)s * nz + cc - 1] : inlet[irow * n + s];
-            }
+          for (int s = 0; s < CAP; ++s) {
+            c[s] = SRC[(size_t)s * nz + cc];
+            up[s] = (cc > 0) ? SRC[(size_t)s * nz + cc - 1] : inlet[irow * n + s];
+          }
           if constexpr (EXACT) {
-            if constexpr (N > 0) exact_row<N>(sc, fe, ue, dz, c, up, k);
-            else exact_row_scratch(n, sc, fe, ue, dz, c, up, k, my_scratch, sstride);
-          } else if constexpr (ARITH == CHROM_KARITH_STRUCT) {
-            if (structured_row<0>(n, sc, cg, c, up, k)) dense_row_scratch(n, sc, cg, c, up, k, my_scratch, sstride);
+            exact_row<N>(sc, fe, ue, dz, c, up, k);
           } else {
             // speculative exchange-free LU; a warp with a flagged cell redoes it with the row-exchanging LU
-            constexpr int NN = N > 0 ? N : 1;
-            const bool redo = fast_row_spec<NN>(sc, c, up, k);
+            const bool redo = fast_row_spec<N>(sc, c, up, k);
             if (__any_sync(0xffffffffu, redo)) {
-              bad |= cold_cell<NN>(sc, fe, cg, SRC, inlet + irow * n, cc, live, st);
+              bad |= cold_cell<N>(sc, fe, cg, SRC, inlet + irow * n, cc, live, st);
               continue;
             }
           }
           if (live) bad |= apply_stage<N, EXACT>(st, cc, k, n);
         }
       }
-      if constexpr (ARITH == CHROM_KARITH_STRUCT && N > 0) {
+      if constexpr (ARITH == CHROM_KARITH_STRUCT) {
         // cold pass: redo the flagged cells with the dense row-exchanging LU (whole warps, out of line)
         if (__any_sync(0xffffffffu, redo_mask != 0u)) {
           for (int ci = 0; ci < cpt; ++ci) {
@@ -871,7 +655,7 @@ __global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_reside
             if (!__any_sync(0xffffffffu, mine)) continue;
             const uint32_t cell = (uint32_t)tid + (uint32_t)ci * T;
             const bool live = cell < nz;
-            bad |= cold_cell<(N > 0 ? N : 1)>(sc, fe, cg, SRC, inlet + irow * n, live ? cell : nz - 1, mine && live, st);
+            bad |= cold_cell<N>(sc, fe, cg, SRC, inlet + irow * n, live ? cell : nz - 1, mine && live, st);
           }
         }
       }
@@ -952,18 +736,21 @@ __global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_reside
   }
 }
 
-typedef void (*mkern_t)(const BatchDev, double*);
+typedef void (*mkern_t)(const BatchDev);
 
 template <int N>
 mkern_t pick_n(int method, int arith) {
-  if (method == CHROM_RK4) {
-    if (arith == CHROM_ARITH_EXACT) return k_multi_resident<N, CHROM_RK4, CHROM_ARITH_EXACT>;
-    if (arith == CHROM_KARITH_STRUCT) return k_multi_resident<N, CHROM_RK4, CHROM_KARITH_STRUCT>;
-    return N > 0 ? k_multi_resident<(N > 0 ? N : 1), CHROM_RK4, CHROM_ARITH_FAST> : nullptr;
+  if constexpr (N >= 1 && N <= 8) {
+    if (method == CHROM_RK4) {
+      if (arith == CHROM_ARITH_EXACT) return k_multi_resident<N, CHROM_RK4, CHROM_ARITH_EXACT>;
+      if (arith == CHROM_KARITH_STRUCT) return k_multi_resident<N, CHROM_RK4, CHROM_KARITH_STRUCT>;
+      return k_multi_resident<N, CHROM_RK4, CHROM_ARITH_FAST>;
+    }
+    if (arith == CHROM_ARITH_EXACT) return k_multi_resident<N, CHROM_EULER, CHROM_ARITH_EXACT>;
+    if (arith == CHROM_KARITH_STRUCT) return k_multi_resident<N, CHROM_EULER, CHROM_KARITH_STRUCT>;
+    return k_multi_resident<N, CHROM_EULER, CHROM_ARITH_FAST>;
   }
-  if (arith == CHROM_ARITH_EXACT) return k_multi_resident<N, CHROM_EULER, CHROM_ARITH_EXACT>;
-  if (arith == CHROM_KARITH_STRUCT) return k_multi_resident<N, CHROM_EULER, CHROM_KARITH_STRUCT>;
-  return N > 0 ? k_multi_resident<(N > 0 ? N : 1), CHROM_EULER, CHROM_ARITH_FAST> : nullptr;
+  return nullptr;
 }
 
 }  // namespace

@@ -9,8 +9,7 @@
 
 namespace chrom {
 
-typedef void (*mkern_t)(const BatchDev, double*);
-mkern_t multi_pick_0(int method, int arith);  // runtime n (9 .. 64)
+typedef void (*mkern_t)(const BatchDev);
 mkern_t multi_pick_1(int method, int arith);
 mkern_t multi_pick_2(int method, int arith);
 mkern_t multi_pick_3(int method, int arith);
@@ -21,8 +20,6 @@ mkern_t multi_pick_7(int method, int arith);
 mkern_t multi_pick_8(int method, int arith);
 
 namespace {
-
-constexpr int kNMax = 64;  // largest runtime n (multi_kernels.cuh)
 
 // bytes of one SpeciesConst in shared memory (multi_kernels.cuh: 10 doubles, 16-byte aligned)
 constexpr size_t kSpeciesConstBytes = 10 * sizeof(double);
@@ -42,7 +39,7 @@ mkern_t lookup_multi(int n, int method, int arith) {
     case 7: return multi_pick_7(method, arith);
     case 8: return multi_pick_8(method, arith);
   }
-  return (n >= 9 && n <= kNMax) ? multi_pick_0(method, arith) : nullptr;
+  return nullptr;
 }
 
 size_t multi_smem_bytes(int n, uint32_t nz) {
@@ -59,24 +56,11 @@ int multi_kernel_arith(int n, int arith) {
   return CHROM_KARITH_STRUCT;
 }
 
-// doubles of per-thread scratch the chosen kernel needs (0 for the register-only variants)
-size_t multi_scratch_per_thread(int n, int karith) {
-  if (n <= 8) return 0;
-  return karith == CHROM_ARITH_EXACT ? (size_t)3 * n * n : (size_t)n * n;
-}
-
 bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why) {
   const int n = (int)b.n_species;
-  if (n < 1 || n > kNMax) {
-    if (why) *why = "n_species outside 1..64";
+  if (n < 1 || n > 8) {  // thread-per-cell kernels hold the n x n system in registers
+    if (why) *why = "n_species > 8 runs one warp per cell (multi_tiled)";
     return false;
-  }
-  if (n > 8) {  // the warp-per-cell kernels of multi_tiled.cu are faster; the runtime-n kernels here are opt-in
-    const char* e = getenv("CHROM_MULTI_THREAD_CELL");
-    if (!(e && atoi(e) != 0)) {
-      if (why) *why = "n_species > 8 runs one warp per cell (multi_tiled)";
-      return false;
-    }
   }
   const size_t smem = multi_smem_bytes(n, b.nz);
   if (smem > 227u * 1024u) {
@@ -84,14 +68,14 @@ bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::
     return false;
   }
   const int karith = b.arith;  // already resolved by multi_kernel_arith
-  const int tmax = n <= 8 ? multi_max_threads(n, karith) : 256;
+  const int tmax = multi_max_threads(n, karith);
   int T = (int)std::min<uint32_t>((b.nz + 31u) / 32u * 32u, (uint32_t)tmax);
   // balance: fewest threads that keep the same number of cells per thread
   const int cpt = (int)((b.nz + T - 1) / T);
   T = (int)(((b.nz + cpt - 1) / cpt + 31u) / 32u * 32u);
   int ctas_per_sm;
   {
-    const int regs = (n > 8) ? 255 : (karith == CHROM_KARITH_STRUCT ? 128 : (n >= 8 ? 232 : (n >= 5 ? 200 : 128)));
+    const int regs = karith == CHROM_KARITH_STRUCT ? 128 : (n >= 8 ? 232 : (n >= 5 ? 200 : 128));
     const int by_smem = (int)((227u * 1024u) / (smem + 1024));
     const int by_regs = 65536 / (T * regs);
     ctas_per_sm = std::max(1, std::min(by_smem, by_regs));
@@ -106,8 +90,8 @@ bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::
   g->grid = dim3(std::min<uint32_t>(b.n_cols, g->cols_per_wave));
   g->smem = smem;
   char buf[240];
-  snprintf(buf, sizeof buf, "multi_resident<n=%d%s,%s,%s> threads/col=%d cells/thread=%d smem=%zuB persistent grid=%u", n,
-           n > 8 ? "(runtime)" : "", b.method == CHROM_RK4 ? "RK4" : "Euler",
+  snprintf(buf, sizeof buf, "multi_resident<n=%d,%s,%s> threads/col=%d cells/thread=%d smem=%zuB persistent grid=%u", n,
+           b.method == CHROM_RK4 ? "RK4" : "Euler",
            karith == CHROM_ARITH_EXACT ? "exact" : (karith == CHROM_KARITH_STRUCT ? "fast-structured-LU" : "fast-dense-LU"),
            T, cpt, smem, g->grid.x);
   g->name = buf;
@@ -120,7 +104,7 @@ cudaError_t multi_resident_launch(const BatchDev& b, const LaunchGeom& g, cudaSt
   cudaError_t e = cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return e;
   const uint32_t grid = std::min<uint32_t>(b.n_cols, g.cols_per_wave ? g.cols_per_wave : b.n_cols);
-  k<<<dim3(grid), g.block, g.smem, s>>>(b, b.scratch);
+  k<<<dim3(grid), g.block, g.smem, s>>>(b);
   return cudaGetLastError();
 }
 

@@ -24,7 +24,7 @@ void multi_tiled_finalize_launch(const BatchDev& b, const unsigned long long* co
 
 namespace {
 
-constexpr int kThreadCellNMax = 64;  // thread per cell: local arrays of multi_kernels.cuh
+constexpr int kThreadCellNMax = 8;   // thread per cell: the n x n system in one thread's registers
 constexpr int kWarpCellNMax = 256;   // warp per cell: 8 species per lane
 constexpr size_t kSmemMax = 227u * 1024u;
 
@@ -40,7 +40,7 @@ tkern_t lookup_tiled(int n, int method, int arith, int wj) {
     case 7: return multi_tiled_pick_7(method, arith, 0);
     case 8: return multi_tiled_pick_8(method, arith, 0);
   }
-  return (n >= 9 && n <= kThreadCellNMax) ? multi_tiled_pick_0(method, arith, 0) : nullptr;
+  return nullptr;
 }
 
 // shared memory of one tile: 4 state arrays [n][pitch], inlet [3][n], summary [n][5], SpeciesConst [n], table pointers [n]
@@ -63,7 +63,7 @@ size_t multi_tiled_scratch_doubles(const BatchDev& b, const LaunchGeom& g) {
     const size_t per_warp = (b.arith == CHROM_ARITH_EXACT ? 2 : 1) * n * n + n;
     return per_warp * g.grid.x * (g.block.x / 32);
   }
-  return multi_scratch_per_thread((int)n, b.arith) * g.grid.x * g.block.x;
+  return 0;  // thread per cell: registers only
 }
 
 // Environment knobs (experiments and tests): CHROM_TILED_WARP=1 warp per cell also for n = 5..8,
@@ -77,10 +77,9 @@ bool multi_tiled_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::str
   const bool rk4 = b.method == CHROM_RK4;
   int wj = 0;
   // n <= 8: thread per cell with the matrix in registers (n <= 4 always: nalgebra inverts those with closed
-  // forms, which are per-thread code).  n >= 9: warp per cell — measured 3-7x faster than the runtime-n
-  // thread-per-cell kernels (n = 12..64, FAST) and 1.2-6x in EXACT mode; CHROM_MULTI_THREAD_CELL=1 opts back.
-  const bool thread_cell = n <= 8 ? !(n >= 5 && env_int("CHROM_TILED_WARP", 0) != 0)
-                                  : (n <= kThreadCellNMax && env_int("CHROM_MULTI_THREAD_CELL", 0) != 0);
+  // forms, which are per-thread code).  n >= 9: warp per cell (measured 9-20x faster than thread-per-cell kernels
+  // with the system in local memory, which were removed).
+  const bool thread_cell = n <= kThreadCellNMax && !(n >= 5 && env_int("CHROM_TILED_WARP", 0) != 0);
   if (!thread_cell) wj = n <= 32 ? 1 : (n <= 64 ? 2 : (n <= 128 ? 4 : 8));
   const int karith = b.arith;
   int T;

@@ -11,8 +11,8 @@
 //    correctly, by the previous tile: no inter-CTA communication.  Tile 0 starts at the inlet and keeps
 //    everything.  A column that fits ONE tile runs all its time steps in a single launch (this is how
 //    n > 64 runs resident).  Algorithmic HBM traffic: 16 * n bytes per cell-step.
-//  * THREAD PER CELL (WJ == 0, n <= 64): the per-cell solvers of multi_kernels.cuh, unchanged.
-//  * WARP PER CELL (WJ > 0, n <= 32 * WJ, default for n > 64): a warp owns one cell, lane l holds the
+//  * THREAD PER CELL (WJ == 0, n <= 8): the per-cell solvers of multi_kernels.cuh, unchanged.
+//  * WARP PER CELL (WJ > 0, n <= 32 * WJ, every n >= 9): a warp owns one cell, lane l holds the
 //    species l, l + 32, ...  FAST: the elimination of A = diag(alpha) - p q^T collapses to scans —
 //    eliminating species 0..i-1 leaves the pivot d_i = alpha_i - p_i q_i / h_i with
 //    h_i = 1 - sum_{j<i} p_j q_j / alpha_j (an exclusive prefix sum over the warp), the partial-pivoting
@@ -257,7 +257,7 @@ __device__ __forceinline__ unsigned warp_cells_fast(int n, int lane, const doubl
 // ---- warp per cell, EXACT: compute_row with nalgebra's LU inverse and gemv -----------------------------
 // scratch: A (the matrix, then its LU) column-major n*n, O (inverse) ROW-major n*n.  Lanes run over rows in
 // the elimination and over columns of O in the triangular solves; each element sees the operations of
-// exact_row_scratch / the oracle in the same order.
+// exact_row / the oracle in the same order.
 template <int WJ>
 __device__ __noinline__ void warp_cell_exact(int n, int lane, const SpeciesConst* sc, double fe, double ue, double dz,
                                              const double* SRC, const double* inlet_row, uint32_t pitch, uint32_t cc,
@@ -400,7 +400,6 @@ __global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi
     k_multi_tiled(const BatchDev b, double* scratch, const TiledArgs a) {
   constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
   constexpr bool EXACT = (ARITH == CHROM_ARITH_EXACT);
-  constexpr int CAP = N > 0 ? N : kNMax;
   constexpr int WJC = WJ > 0 ? WJ : 1;
   extern __shared__ double smem[];
   const int n = N > 0 ? N : (int)b.n_species;
@@ -416,8 +415,6 @@ __global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi
   double* summ = inlet + 3 * n;                      // [n][5]
   SpeciesConst* sc = (SpeciesConst*)(summ + 5 * n);  // [n]
   const double** tabs = (const double**)(sc + n);    // [n]
-  const size_t sstride = (size_t)gridDim.x * T;      // thread-per-cell scratch: element e at my_scratch[e * sstride]
-  double* my_scratch = scratch ? scratch + (size_t)blockIdx.x * T + tid : nullptr;
   double* warp_scratch = nullptr;                    // warp-per-cell scratch: a contiguous block per warp
   if (WJ > 0 && scratch)
     warp_scratch = scratch + ((size_t)blockIdx.x * W + warp) * ((size_t)(EXACT ? 2 : 1) * n * n + n);
@@ -553,7 +550,7 @@ __global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi
             }
           }
         }
-      } else {
+      } else if constexpr (N > 0) {  // thread per cell: the n x n system of a cell in one thread's registers
         const int cpt = (int)((a.tw + T - 1) / T);
         unsigned redo_mask = 0u;
         for (int ci = 0; ci < cpt; ++ci) {
@@ -561,36 +558,31 @@ __global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi
           const bool live = cell < ncell;
           const uint32_t cc = live ? cell : ncell - 1;  // idle lanes recompute the last cell, never store
           const bool owned = live && cc >= first_valid;
-          double k[CAP];
-          if constexpr (ARITH == CHROM_KARITH_STRUCT && N > 0) {
-            const bool redo = scan_cell<(N > 0 ? N : 1)>(sc, cg, SRC, inlet_row, pitch, cc, k);
+          double k[N];
+          if constexpr (ARITH == CHROM_KARITH_STRUCT) {
+            const bool redo = scan_cell<N>(sc, cg, SRC, inlet_row, pitch, cc, k);
             if (redo) redo_mask |= 1u << ci;
             else if (live) bad |= apply_stage<N, false>(st, cc, k, n) && owned;
           } else {
-            double c[CAP], up[CAP];
+            double c[N], up[N];
 #pragma unroll
-            for (int s = 0; s < CAP; ++s)
-              if (s < n) {
-                c[s] = SRC[(size_t)s * pitch + cc];
-                up[s] = (cc > 0) ? SRC[(size_t)s * pitch + cc - 1] : inlet_row[s];
-              }
+            for (int s = 0; s < N; ++s) {
+              c[s] = SRC[(size_t)s * pitch + cc];
+              up[s] = (cc > 0) ? SRC[(size_t)s * pitch + cc - 1] : inlet_row[s];
+            }
             if constexpr (EXACT) {
-              if constexpr (N > 0) exact_row<(N > 0 ? N : 1)>(sc, fe, ue, dz, c, up, k);
-              else exact_row_scratch(n, sc, fe, ue, dz, c, up, k, my_scratch, sstride);
-            } else if constexpr (ARITH == CHROM_KARITH_STRUCT) {
-              if (structured_row<0>(n, sc, cg, c, up, k)) dense_row_scratch(n, sc, cg, c, up, k, my_scratch, sstride);
+              exact_row<N>(sc, fe, ue, dz, c, up, k);
             } else {
-              constexpr int NN = N > 0 ? N : 1;
-              const bool redo = fast_row_spec<NN>(sc, c, up, k);
+              const bool redo = fast_row_spec<N>(sc, c, up, k);
               if (__any_sync(kFull, redo)) {
-                bad |= cold_cell<NN>(sc, fe, cg, SRC, inlet_row, cc, live, st) && owned;
+                bad |= cold_cell<N>(sc, fe, cg, SRC, inlet_row, cc, live, st) && owned;
                 continue;
               }
             }
             if (live) bad |= apply_stage<N, EXACT>(st, cc, k, n) && owned;
           }
         }
-        if constexpr (ARITH == CHROM_KARITH_STRUCT && N > 0) {
+        if constexpr (ARITH == CHROM_KARITH_STRUCT) {
           if (__any_sync(kFull, redo_mask != 0u)) {
             for (int ci = 0; ci < cpt; ++ci) {
               const bool mine = (redo_mask >> ci) & 1u;
@@ -598,8 +590,7 @@ __global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi
               const uint32_t cell = (uint32_t)tid + (uint32_t)ci * T;
               const bool live = cell < ncell;
               const uint32_t cc = live ? cell : ncell - 1;
-              bad |= cold_cell<(N > 0 ? N : 1)>(sc, fe, cg, SRC, inlet_row, cc, mine && live, st) &&
-                     (live && cc >= first_valid);
+              bad |= cold_cell<N>(sc, fe, cg, SRC, inlet_row, cc, mine && live, st) && (live && cc >= first_valid);
             }
           }
         }
@@ -716,18 +707,21 @@ __global__ void k_tiled_finalize(const BatchDev b, const unsigned long long* __r
 
 typedef void (*tkern_t)(const BatchDev, double*, const TiledArgs);
 
-// thread per cell (wj == 0) for every N; warp per cell (wj = 1, 2, 4, 8) only in the runtime-n object
+// thread per cell (wj == 0) for N = 1..8; warp per cell (wj = 1, 2, 4, 8) in the runtime-n object (N == 0)
 template <int N>
 tkern_t pick_tiled_n(int method, int arith, int wj) {
   if (wj == 0) {
-    if (method == CHROM_RK4) {
-      if (arith == CHROM_ARITH_EXACT) return k_multi_tiled<N, CHROM_RK4, CHROM_ARITH_EXACT, 0>;
-      if (arith == CHROM_KARITH_STRUCT) return k_multi_tiled<N, CHROM_RK4, CHROM_KARITH_STRUCT, 0>;
-      return N > 0 ? k_multi_tiled<(N > 0 ? N : 1), CHROM_RK4, CHROM_ARITH_FAST, 0> : nullptr;
+    if constexpr (N >= 1 && N <= 8) {
+      if (method == CHROM_RK4) {
+        if (arith == CHROM_ARITH_EXACT) return k_multi_tiled<N, CHROM_RK4, CHROM_ARITH_EXACT, 0>;
+        if (arith == CHROM_KARITH_STRUCT) return k_multi_tiled<N, CHROM_RK4, CHROM_KARITH_STRUCT, 0>;
+        return k_multi_tiled<N, CHROM_RK4, CHROM_ARITH_FAST, 0>;
+      }
+      if (arith == CHROM_ARITH_EXACT) return k_multi_tiled<N, CHROM_EULER, CHROM_ARITH_EXACT, 0>;
+      if (arith == CHROM_KARITH_STRUCT) return k_multi_tiled<N, CHROM_EULER, CHROM_KARITH_STRUCT, 0>;
+      return k_multi_tiled<N, CHROM_EULER, CHROM_ARITH_FAST, 0>;
     }
-    if (arith == CHROM_ARITH_EXACT) return k_multi_tiled<N, CHROM_EULER, CHROM_ARITH_EXACT, 0>;
-    if (arith == CHROM_KARITH_STRUCT) return k_multi_tiled<N, CHROM_EULER, CHROM_KARITH_STRUCT, 0>;
-    return N > 0 ? k_multi_tiled<(N > 0 ? N : 1), CHROM_EULER, CHROM_ARITH_FAST, 0> : nullptr;
+    return nullptr;
   }
   if constexpr (N == 0) {
     const bool ex = arith == CHROM_ARITH_EXACT;

@@ -110,13 +110,10 @@ def test_species_counts_exact_and_fast(ctx, n, nz):
 
 @pytest.mark.parametrize("n", [9, 12, 16, 24, 40])
 @pytest.mark.parametrize("method", [cb.RK4, cb.EULER], ids=["rk4", "euler"])
-@pytest.mark.parametrize("path", ["warp", "thread"])
-def test_many_species_runtime_n(ctx, monkeypatch, n, method, path):
-    """n > 8: runtime-n kernels.  Default: one warp per cell (multi_tiled.cu).  CHROM_MULTI_THREAD_CELL=1: one thread
-    per cell, EXACT = nalgebra LU restated on per-thread scratch matrices (bit-identical), FAST = structured LU in
-    O(n) scalars (dense pivoted LU on scratch when a row exchange is needed)."""
-    if path == "thread":
-        monkeypatch.setenv("CHROM_MULTI_THREAD_CELL", "1")
+def test_many_species_runtime_n(ctx, n, method):
+    """n > 8: one warp per cell (multi_tiled.cu).  EXACT = nalgebra LU + gemv restated with lanes over rows /
+    columns (bit-identical), FAST = the closed-form structured elimination (dense row-exchanging LU on a scratch
+    matrix when a row exchange is needed)."""
     nz, steps, T = 40, 60, 6.0
     rng = np.random.default_rng(1000 + n)
     y0 = rng.uniform(0.0, 0.05, size=(nz, n))
