@@ -88,7 +88,7 @@ bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::
 cudaError_t multi_resident_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s);
 int multi_kernel_arith(int n_species, int arith);
 
-// multi_reg.cu — LangmuirMulti n <= 8 with the state in registers (FAST arithmetic)
+// multi_reg.cu — LangmuirMulti n <= 16 with the state in registers (FAST arithmetic)
 bool multi_reg_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why);
 cudaError_t multi_reg_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s);
 

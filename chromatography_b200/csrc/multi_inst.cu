@@ -1,4 +1,4 @@
-// multi_inst.cu — one translation unit per species count (compiled with -DCHROM_MULTI_N=0..8, 0 = runtime n)
+// multi_inst.cu — one translation unit per species count (compiled with -DCHROM_MULTI_N=0..16, 0 = runtime n)
 // so that the nine instantiation sets of multi_kernels.cuh / multi_tiled.cuh build in parallel.
 #include "multi_reg.cuh"
 #include "multi_tiled.cuh"
@@ -9,12 +9,14 @@
 namespace chrom {
 typedef void (*mkern_t)(const BatchDev);
 typedef void (*tkern_t)(const BatchDev, double*, const TiledArgs);
+typedef void (*rkern_t)(const BatchDev);
+#if CHROM_MULTI_N <= 8  // shared-memory-resident and tiled kernels: n = 1..8 per thread, runtime n (0) per warp
 mkern_t CHROM_CAT(multi_pick_, CHROM_MULTI_N)(int method, int arith) { return pick_n<CHROM_MULTI_N>(method, arith); }
 tkern_t CHROM_CAT(multi_tiled_pick_, CHROM_MULTI_N)(int method, int arith, int wj) {
   return pick_tiled_n<CHROM_MULTI_N>(method, arith, wj);
 }
-#if CHROM_MULTI_N > 0
-typedef void (*rkern_t)(const BatchDev);
+#endif
+#if CHROM_MULTI_N > 0  // register-resident kernels: n = 1..16
 rkern_t CHROM_CAT(multi_reg_pick_, CHROM_MULTI_N)(int method, int m) { return pick_reg_n<CHROM_MULTI_N>(method, m); }
 int CHROM_CAT(multi_reg_tmax_, CHROM_MULTI_N)(int m) {  // threads per CTA; negative: acc lives in shared memory
   const int t = reg_max_threads_rt<CHROM_MULTI_N>(m);

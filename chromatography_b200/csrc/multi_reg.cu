@@ -12,6 +12,7 @@ typedef void (*rkern_t)(const BatchDev);
   rkern_t multi_reg_pick_##N(int method, int m); \
   int multi_reg_tmax_##N(int m);
 CHROM_DECL(1) CHROM_DECL(2) CHROM_DECL(3) CHROM_DECL(4) CHROM_DECL(5) CHROM_DECL(6) CHROM_DECL(7) CHROM_DECL(8)
+CHROM_DECL(9) CHROM_DECL(10) CHROM_DECL(11) CHROM_DECL(12) CHROM_DECL(13) CHROM_DECL(14) CHROM_DECL(15) CHROM_DECL(16)
 #undef CHROM_DECL
 
 namespace {
@@ -26,6 +27,14 @@ rkern_t lookup_reg(int n, int method, int m) {
     case 6: return multi_reg_pick_6(method, m);
     case 7: return multi_reg_pick_7(method, m);
     case 8: return multi_reg_pick_8(method, m);
+    case 9: return multi_reg_pick_9(method, m);
+    case 10: return multi_reg_pick_10(method, m);
+    case 11: return multi_reg_pick_11(method, m);
+    case 12: return multi_reg_pick_12(method, m);
+    case 13: return multi_reg_pick_13(method, m);
+    case 14: return multi_reg_pick_14(method, m);
+    case 15: return multi_reg_pick_15(method, m);
+    case 16: return multi_reg_pick_16(method, m);
   }
   return nullptr;
 }
@@ -40,6 +49,14 @@ int tmax_reg(int n, int m) {
     case 6: return multi_reg_tmax_6(m);
     case 7: return multi_reg_tmax_7(m);
     case 8: return multi_reg_tmax_8(m);
+    case 9: return multi_reg_tmax_9(m);
+    case 10: return multi_reg_tmax_10(m);
+    case 11: return multi_reg_tmax_11(m);
+    case 12: return multi_reg_tmax_12(m);
+    case 13: return multi_reg_tmax_13(m);
+    case 14: return multi_reg_tmax_14(m);
+    case 15: return multi_reg_tmax_15(m);
+    case 16: return multi_reg_tmax_16(m);
   }
   return 0;
 }
@@ -49,8 +66,8 @@ int tmax_reg(int n, int m) {
 // Cells per thread M in {1, 2, 4}; CHROM_REG_M overrides (experiments).
 bool multi_reg_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why) {
   const int n = (int)b.n_species;
-  if (n < 1 || n > 8) {
-    if (why) *why = "register-resident multi kernel covers n_species 1..8";
+  if (n < 1 || n > 16) {
+    if (why) *why = "register-resident multi kernel covers n_species 1..16";
     return false;
   }
   const char* force = getenv("CHROM_REG_M");
@@ -60,7 +77,7 @@ bool multi_reg_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::strin
   // the most threads per column (1 cell per thread).
   const bool fills = (uint64_t)b.n_cols >= (uint64_t)sm_count * 2u;
   const int order_small[3] = {2, 1, 4}, order_large[3] = {1, 2, 4}, order_latency[3] = {1, 2, 4};
-  const int* order = !fills ? order_latency : (n <= 4 ? order_small : order_large);
+  const int* order = !fills ? order_latency : (n <= 4 ? order_small : order_large);  // n > 12: only M = 1 exists
   for (int oi = 0; oi < 3; ++oi) {
     const int M = order[oi];
     if (force && atoi(force) != M) continue;

@@ -1,4 +1,4 @@
-// multi_reg.cuh — register-resident LangmuirMulti time integrator (RK4 / Euler), n <= 8, FAST arithmetic.
+// multi_reg.cuh — register-resident LangmuirMulti time integrator (RK4 / Euler), n <= 16, FAST arithmetic.
 //
 // Replaces, for a batch of columns and ALL time steps in one launch, the same reference code as
 // multi_kernels.cuh (rk4.rs:266-332, euler.rs:227-269, langmuir_multi.rs:627-686, 717-899,
@@ -367,16 +367,17 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
 
 typedef void (*rkern_t)(const BatchDev);
 
+// cells per thread: 1 for every n <= 16, 2 for n <= 12, 4 for n <= 4 (register file)
 template <int N>
 rkern_t pick_reg_n(int method, int m) {
-  if constexpr (N >= 1 && N <= 8) {
+  if constexpr (N >= 1 && N <= 16) {
     const bool rk4 = method == CHROM_RK4;
-    switch (m) {
-      case 1: return rk4 ? k_multi_reg<N, 1, CHROM_RK4> : k_multi_reg<N, 1, CHROM_EULER>;
-      case 2: return rk4 ? k_multi_reg<N, 2, CHROM_RK4> : k_multi_reg<N, 2, CHROM_EULER>;
-      case 4:
-        if constexpr (N <= 4) return rk4 ? k_multi_reg<N, 4, CHROM_RK4> : k_multi_reg<N, 4, CHROM_EULER>;
-        break;
+    if (m == 1) return rk4 ? k_multi_reg<N, 1, CHROM_RK4> : k_multi_reg<N, 1, CHROM_EULER>;
+    if constexpr (N <= 12) {
+      if (m == 2) return rk4 ? k_multi_reg<N, 2, CHROM_RK4> : k_multi_reg<N, 2, CHROM_EULER>;
+    }
+    if constexpr (N <= 4) {
+      if (m == 4) return rk4 ? k_multi_reg<N, 4, CHROM_RK4> : k_multi_reg<N, 4, CHROM_EULER>;
     }
   }
   return nullptr;
@@ -384,9 +385,9 @@ rkern_t pick_reg_n(int method, int m) {
 
 template <int N>
 bool reg_acc_shared_rt(int m) {
-  if constexpr (N >= 1 && N <= 8) {
+  if constexpr (N >= 1 && N <= 16) {
     if (m == 1) return reg_acc_shared(N, 1);
-    if (m == 2) return reg_acc_shared(N, 2);
+    if (m == 2 && N <= 12) return reg_acc_shared(N, 2);
     if (m == 4 && N <= 4) return reg_acc_shared(N, 4);
   }
   return false;
@@ -394,9 +395,9 @@ bool reg_acc_shared_rt(int m) {
 
 template <int N>
 int reg_max_threads_rt(int m) {
-  if constexpr (N >= 1 && N <= 8) {
+  if constexpr (N >= 1 && N <= 16) {
     if (m == 1) return reg_max_threads(N, 1);
-    if (m == 2) return reg_max_threads(N, 2);
+    if (m == 2 && N <= 12) return reg_max_threads(N, 2);
     if (m == 4 && N <= 4) return reg_max_threads(N, 4);
   }
   return 0;
