@@ -33,6 +33,27 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in _ffi.lib().chrom_cuda_version()
 
 
+def test_constants_match_header():
+    """Every CHROM_* constant of include/chrom_cuda.h equals its mirror in the ctypes table and the C++ host enum."""
+    src = open(os.path.join(ROOT, "include", "chrom_cuda.h")).read()
+    defs = {k: int(v.strip("()u")) for k, v in re.findall(r"#define (CHROM_[A-Z0-9_]+) (\(?-?\d+u?\)?)", src)}
+    mirror = {"CHROM_OK": _ffi.CHROM_OK, "CHROM_EULER": _ffi.EULER, "CHROM_RK4": _ffi.RK4,
+              "CHROM_ARITH_FAST": _ffi.ARITH_FAST, "CHROM_ARITH_EXACT": _ffi.ARITH_EXACT,
+              "CHROM_ARITH_FAST_STRUCTURED": _ffi.ARITH_FAST_STRUCTURED, "CHROM_ARITH_FAST_DENSE": _ffi.ARITH_FAST_DENSE,
+              "CHROM_WANT_OUTLET": _ffi.WANT_OUTLET, "CHROM_WANT_SNAPSHOTS": _ffi.WANT_SNAPSHOTS,
+              "CHROM_WANT_FINAL": _ffi.WANT_FINAL, "CHROM_WANT_SUMMARY": _ffi.WANT_SUMMARY,
+              "CHROM_WANT_STATUS": _ffi.WANT_STATUS}
+    for k, v in mirror.items():
+        assert defs[k] == v, (k, defs[k], v)
+    hpp = open(os.path.join(ROOT, "include", "chrom", "solver.hpp")).read()
+    for name, key in (("Fast", "CHROM_ARITH_FAST"), ("Exact", "CHROM_ARITH_EXACT"),
+                      ("FastStructured", "CHROM_ARITH_FAST_STRUCTURED"), ("FastDense", "CHROM_ARITH_FAST_DENSE")):
+        assert re.search(rf"\b{name} = {defs[key]},", hpp), name
+    rs = open(os.path.join(ROOT, "bindings", "rust", "chrom-cuda", "src", "ffi.rs")).read()
+    for key in ("CHROM_ARITH_FAST", "CHROM_ARITH_EXACT", "CHROM_ARITH_FAST_STRUCTURED", "CHROM_ARITH_FAST_DENSE"):
+        assert re.search(rf"pub const {key}: i32 = {defs[key]};", rs), key
+
+
 def test_struct_layouts_match_header():
     assert C.sizeof(_ffi.SingleCol) == 56 and C.sizeof(_ffi.MultiCol) == 40 and C.sizeof(_ffi.Species) == 24
     assert C.sizeof(_ffi.RunCfg) == 48 and C.sizeof(_ffi.Timing) == 56
