@@ -248,3 +248,35 @@ def test_ragged_grid_sizes(ctx, n, nz):
             for k in range(n):
                 area = O.trapezoid(ref.time_points, ref.outlet[k])
                 assert abs(f.summary[c][k][0] - area) <= MOMENT_RTOL * abs(area)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomised_strongly_nonlinear_cases(ctx, seed):
+    """Random species counts, grids, affinities over three decades and loads up to strongly non-linear (K c >> 1):
+    whichever path a cell takes in FAST mode — sufficient bound, per-step pivot test, dense row-exchanging LU —
+    the result must stay within 1e-9 of the oracle and validate_state must agree; EXACT stays bit-identical."""
+    rng = np.random.default_rng(9000 + seed)
+    n = int(rng.choice([2, 3, 5, 8, 11, 16, 20, 33]))
+    nz = int(rng.integers(10, 300))
+    lam = rng.uniform(0.0, 1.5, n)
+    K = np.exp(rng.uniform(np.log(0.05), np.log(50.0), n))
+    ports = rng.integers(1, 4, n)
+    conc = rng.uniform(0.01, 2.0)
+    inj = cb.TemporalInjection.rectangle(0.0, 0.5, conc)
+    sp = [cb.SpeciesParams.new(f"S{k}", float(lam[k]), float(K[k]), int(ports[k]), inj) for k in range(n)]
+    m = cb.LangmuirMulti.new(sp, nz, 0.4, 1e-3, 0.25 * nz / 100.0)
+    y0 = rng.uniform(0.0, 1.0, size=(nz, n)) * (rng.uniform(size=(1, n)) < 0.7)  # some species absent at first
+    steps, T = 40, 40 * 0.2 * m.dz / m.ue  # CFL 0.2 on the unretained velocity
+    om = to_oracle(m)
+    ref = O.solve_multi(om, O.RK4, T, steps, y0=y0)
+    y0_dev = np.ascontiguousarray(y0.T)[None]
+    e = run_gpu(ctx, [m], cb.RK4, T, steps, cb.ARITH_EXACT, y0=y0_dev)
+    assert e.status[0] == ref.status
+    if ref.status == 0:
+        assert_bit_equal(e.final_state[0].T, ref.final_state, f"seed {seed}: n={n} nz={nz} exact")
+    for arith in (cb.ARITH_FAST,) + ((cb.ARITH_FAST_DENSE,) if n <= 8 else ()):
+        f = run_gpu(ctx, [m], cb.RK4, T, steps, arith, y0=y0_dev)
+        assert f.status[0] == ref.status
+        if ref.status == 0:
+            assert max_rel_err(f.final_state[0].T, ref.final_state) <= PROFILE_RTOL, (seed, n, nz, arith)
+            assert max_rel_err(f.outlet[0], ref.outlet) <= PROFILE_RTOL, (seed, n, nz, arith)
