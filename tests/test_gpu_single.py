@@ -329,3 +329,41 @@ def test_time_sliced_last_chunk(ctx, method, stride):
     oo, of, _ = O.solve_single_batch([to_oracle(models[i]) for i in pick], om, T, steps)
     assert_bit_equal(one.outlet[pick], oo[:, ::stride], "outlet vs oracle")
     assert_bit_equal(one.final_state[pick], of, "final vs oracle")
+
+
+@pytest.mark.parametrize("method", ["rk4", "euler"])
+def test_randomised_isotherms_including_extremely_steep(ctx, monkeypatch, method):
+    """Random LangmuirSingle columns over wide parameter ranges, loads up to K c >> 1, and isotherms so steep
+    (fe nbar K / (1 + fe lambda) > 1e3) that the host must drop the polynomial FAST form (which subtracts two nearly
+    equal numbers there) for the cancellation-free one; a batch mixing both kinds takes the safe form as a whole.
+    The plan description says which form ran; both stay within 1e-9 of the oracle, EXACT is bit-identical."""
+    gm, om = METHODS[method]
+    rng = np.random.default_rng(77)
+    nz, steps = 120, 60
+    inj = cb.TemporalInjection.rectangle(0.0, 0.3, 0.5)
+
+    def model(k, n_ports, lam):
+        return cb.LangmuirSingle.new(lam, k, n_ports, 0.4, 1e-3, 0.25, nz, inj)
+
+    mild = [model(float(np.exp(rng.uniform(np.log(0.05), np.log(20.0)))), float(rng.uniform(0.5, 3.0)),
+                  float(rng.uniform(0.0, 1.5))) for _ in range(12)]
+    steep = [model(float(rng.uniform(2e3, 2e4)), float(rng.uniform(1.0, 3.0)), 0.0) for _ in range(4)]
+    y0 = rng.uniform(0.0, 1.0, size=(16, nz))
+    T = steps * 0.2 * mild[0].dz / mild[0].ue
+    for name, models in (("mild", mild), ("steep", steep), ("mixed", mild[:4] + steep)):
+        cfg = cb.make_cfg(gm, T, steps, nz, 1, 1, 0, cb.ARITH_FAST)
+        cols, tables = cb.pack_single(models, gm, T, steps)
+        plan = cb.Plan(ctx, cfg, cols, tables, y0=y0[:len(models)])
+        desc = plan.describe()
+        plan.close()
+        assert ("fast-poly" in desc) == (name == "mild"), (name, desc)
+        oo, of, ost = O.solve_single_batch([to_oracle(m) for m in models], om, T, steps, y0=y0[:len(models)])
+        f = run_gpu(ctx, models, gm, T, steps, cb.ARITH_FAST, y0=y0[:len(models)])
+        np.testing.assert_array_equal(f.status, ost)
+        ok = ost == 0
+        assert ok.any()
+        assert max_rel_err(f.final_state[ok], of[ok]) <= PROFILE_RTOL, name
+        assert max_rel_err(f.outlet[ok], oo[ok]) <= PROFILE_RTOL, name
+        e = run_gpu(ctx, models, gm, T, steps, cb.ARITH_EXACT, y0=y0[:len(models)])
+        np.testing.assert_array_equal(e.status, ost)
+        assert_bit_equal(e.final_state[ok], of[ok], f"{name} exact")
