@@ -10,12 +10,11 @@ namespace chrom {
 typedef void (*mkern_t)(const BatchDev);
 typedef void (*tkern_t)(const BatchDev, double*, const TiledArgs);
 typedef void (*rkern_t)(const BatchDev);
-#if CHROM_MULTI_N <= 8  // shared-memory-resident and tiled kernels: n = 1..8 per thread, runtime n (0) per warp
+// shared-memory-resident and tiled kernels: n = 1..8 per thread (9..16: closed form only), runtime n (0) per warp
 mkern_t CHROM_CAT(multi_pick_, CHROM_MULTI_N)(int method, int arith) { return pick_n<CHROM_MULTI_N>(method, arith); }
 tkern_t CHROM_CAT(multi_tiled_pick_, CHROM_MULTI_N)(int method, int arith, int wj) {
   return pick_tiled_n<CHROM_MULTI_N>(method, arith, wj);
 }
-#endif
 #if CHROM_MULTI_N > 0  // register-resident kernels: n = 1..16
 rkern_t CHROM_CAT(multi_reg_pick_, CHROM_MULTI_N)(int method, int m) { return pick_reg_n<CHROM_MULTI_N>(method, m); }
 int CHROM_CAT(multi_reg_tmax_, CHROM_MULTI_N)(int m) {  // threads per CTA; negative: acc lives in shared memory

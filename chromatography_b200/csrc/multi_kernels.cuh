@@ -538,15 +538,17 @@ __device__ __noinline__ bool cold_cell(const SpeciesConst* sc, double fe, double
 }
 
 // ---- kernel ---------------------------------------------------------------------------------------
-// ARITH: CHROM_ARITH_FAST (dense register LU), CHROM_ARITH_EXACT, CHROM_KARITH_STRUCT.  1 <= N <= 8 (larger
-// species counts run one warp per cell: multi_tiled.cuh).
+// ARITH: CHROM_ARITH_FAST (dense register LU) and CHROM_ARITH_EXACT for 1 <= N <= 8 (the n x n system in one
+// thread's registers); CHROM_KARITH_STRUCT (closed-form elimination, 4 N doubles per thread) for 1 <= N <= 16.
+// Other species counts / modes run one warp per cell (multi_tiled.cuh).
 constexpr int multi_max_threads(int N, int ARITH) {
-  return (ARITH == CHROM_KARITH_STRUCT && N > 0) ? 512 : ((N > 0 && N <= 2) ? 512 : 256);
+  return ARITH == CHROM_KARITH_STRUCT ? (N <= 8 ? 512 : 256) : (N <= 2 ? 512 : 256);
 }
 
 template <int N, int METHOD, int ARITH>
 __global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_resident(const BatchDev b) {
-  static_assert(N >= 1 && N <= 8, "thread-per-cell kernels hold the n x n system in registers");
+  static_assert(N >= 1 && (N <= 8 || (N <= 16 && ARITH == CHROM_KARITH_STRUCT)),
+                "thread-per-cell kernels: dense / exact n <= 8 (matrix in registers), closed form n <= 16");
   constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
   constexpr bool EXACT = (ARITH == CHROM_ARITH_EXACT);
   constexpr int CAP = N;
@@ -749,6 +751,10 @@ mkern_t pick_n(int method, int arith) {
     if (arith == CHROM_ARITH_EXACT) return k_multi_resident<N, CHROM_EULER, CHROM_ARITH_EXACT>;
     if (arith == CHROM_KARITH_STRUCT) return k_multi_resident<N, CHROM_EULER, CHROM_KARITH_STRUCT>;
     return k_multi_resident<N, CHROM_EULER, CHROM_ARITH_FAST>;
+  } else if constexpr (N >= 9 && N <= 16) {
+    if (arith != CHROM_KARITH_STRUCT) return nullptr;
+    return method == CHROM_RK4 ? k_multi_resident<N, CHROM_RK4, CHROM_KARITH_STRUCT>
+                               : k_multi_resident<N, CHROM_EULER, CHROM_KARITH_STRUCT>;
   }
   return nullptr;
 }

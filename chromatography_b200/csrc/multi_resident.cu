@@ -18,14 +18,22 @@ mkern_t multi_pick_5(int method, int arith);
 mkern_t multi_pick_6(int method, int arith);
 mkern_t multi_pick_7(int method, int arith);
 mkern_t multi_pick_8(int method, int arith);
+mkern_t multi_pick_9(int method, int arith);
+mkern_t multi_pick_10(int method, int arith);
+mkern_t multi_pick_11(int method, int arith);
+mkern_t multi_pick_12(int method, int arith);
+mkern_t multi_pick_13(int method, int arith);
+mkern_t multi_pick_14(int method, int arith);
+mkern_t multi_pick_15(int method, int arith);
+mkern_t multi_pick_16(int method, int arith);
 
 namespace {
 
 // bytes of one SpeciesConst in shared memory (multi_kernels.cuh: 10 doubles, 16-byte aligned)
 constexpr size_t kSpeciesConstBytes = 10 * sizeof(double);
 
-constexpr int multi_max_threads(int N, int ARITH) {
-  return (ARITH == CHROM_KARITH_STRUCT && N > 0) ? 512 : ((N > 0 && N <= 2) ? 512 : 256);
+constexpr int multi_max_threads(int N, int ARITH) {  // = multi_kernels.cuh
+  return ARITH == CHROM_KARITH_STRUCT ? (N <= 8 ? 512 : 256) : (N <= 2 ? 512 : 256);
 }
 
 mkern_t lookup_multi(int n, int method, int arith) {
@@ -38,6 +46,14 @@ mkern_t lookup_multi(int n, int method, int arith) {
     case 6: return multi_pick_6(method, arith);
     case 7: return multi_pick_7(method, arith);
     case 8: return multi_pick_8(method, arith);
+    case 9: return multi_pick_9(method, arith);
+    case 10: return multi_pick_10(method, arith);
+    case 11: return multi_pick_11(method, arith);
+    case 12: return multi_pick_12(method, arith);
+    case 13: return multi_pick_13(method, arith);
+    case 14: return multi_pick_14(method, arith);
+    case 15: return multi_pick_15(method, arith);
+    case 16: return multi_pick_16(method, arith);
   }
   return nullptr;
 }
@@ -58,8 +74,9 @@ int multi_kernel_arith(int n, int arith) {
 
 bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why) {
   const int n = (int)b.n_species;
-  if (n < 1 || n > 8) {  // thread-per-cell kernels hold the n x n system in registers
-    if (why) *why = "n_species > 8 runs one warp per cell (multi_tiled)";
+  // thread per cell: dense / exact n <= 8 (the n x n system in registers), closed-form elimination n <= 16
+  if (n < 1 || n > 16 || (n > 8 && b.arith != CHROM_KARITH_STRUCT)) {
+    if (why) *why = "this species count / arithmetic runs one warp per cell (multi_tiled)";
     return false;
   }
   const size_t smem = multi_smem_bytes(n, b.nz);
@@ -75,7 +92,7 @@ bool multi_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::
   T = (int)(((b.nz + cpt - 1) / cpt + 31u) / 32u * 32u);
   int ctas_per_sm;
   {
-    const int regs = karith == CHROM_KARITH_STRUCT ? 128 : (n >= 8 ? 232 : (n >= 5 ? 200 : 128));
+    const int regs = karith == CHROM_KARITH_STRUCT ? (n <= 8 ? 128 : 255) : (n >= 8 ? 232 : (n >= 5 ? 200 : 128));
     const int by_smem = (int)((227u * 1024u) / (smem + 1024));
     const int by_regs = 65536 / (T * regs);
     ctas_per_sm = std::max(1, std::min(by_smem, by_regs));

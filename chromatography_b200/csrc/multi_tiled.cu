@@ -19,12 +19,19 @@ tkern_t multi_tiled_pick_5(int method, int arith, int wj);
 tkern_t multi_tiled_pick_6(int method, int arith, int wj);
 tkern_t multi_tiled_pick_7(int method, int arith, int wj);
 tkern_t multi_tiled_pick_8(int method, int arith, int wj);
+tkern_t multi_tiled_pick_9(int method, int arith, int wj);
+tkern_t multi_tiled_pick_10(int method, int arith, int wj);
+tkern_t multi_tiled_pick_11(int method, int arith, int wj);
+tkern_t multi_tiled_pick_12(int method, int arith, int wj);
+tkern_t multi_tiled_pick_13(int method, int arith, int wj);
+tkern_t multi_tiled_pick_14(int method, int arith, int wj);
+tkern_t multi_tiled_pick_15(int method, int arith, int wj);
+tkern_t multi_tiled_pick_16(int method, int arith, int wj);
 void multi_tiled_init_launch(const BatchDev& b, double* ping, unsigned long long* code, cudaStream_t s);
 void multi_tiled_finalize_launch(const BatchDev& b, const unsigned long long* code, const double* gsumm, cudaStream_t s);
 
 namespace {
 
-constexpr int kThreadCellNMax = 8;   // thread per cell: the n x n system in one thread's registers
 constexpr int kWarpCellNMax = 256;   // warp per cell: 8 species per lane
 constexpr size_t kSmemMax = 227u * 1024u;
 
@@ -39,6 +46,14 @@ tkern_t lookup_tiled(int n, int method, int arith, int wj) {
     case 6: return multi_tiled_pick_6(method, arith, 0);
     case 7: return multi_tiled_pick_7(method, arith, 0);
     case 8: return multi_tiled_pick_8(method, arith, 0);
+    case 9: return multi_tiled_pick_9(method, arith, 0);
+    case 10: return multi_tiled_pick_10(method, arith, 0);
+    case 11: return multi_tiled_pick_11(method, arith, 0);
+    case 12: return multi_tiled_pick_12(method, arith, 0);
+    case 13: return multi_tiled_pick_13(method, arith, 0);
+    case 14: return multi_tiled_pick_14(method, arith, 0);
+    case 15: return multi_tiled_pick_15(method, arith, 0);
+    case 16: return multi_tiled_pick_16(method, arith, 0);
   }
   return nullptr;
 }
@@ -76,15 +91,16 @@ bool multi_tiled_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::str
   }
   const bool rk4 = b.method == CHROM_RK4;
   int wj = 0;
-  // n <= 8: thread per cell with the matrix in registers (n <= 4 always: nalgebra inverts those with closed
-  // forms, which are per-thread code).  n >= 9: warp per cell (measured 9-20x faster than thread-per-cell kernels
-  // with the system in local memory, which were removed).
-  const bool thread_cell = n <= kThreadCellNMax && !(n >= 5 && env_int("CHROM_TILED_WARP", 0) != 0);
+  // Thread per cell: n <= 8 in every mode (n <= 4 always: nalgebra inverts those with closed forms, which are
+  // per-thread code), n = 9..16 for the closed-form FAST elimination (4 n doubles per thread; measured 4x the
+  // warp-per-cell rate).  Everything else one warp per cell.
+  const bool thread_cell = n <= 8 ? !(n >= 5 && env_int("CHROM_TILED_WARP", 0) != 0)
+                                  : (n <= 16 && b.arith == CHROM_KARITH_STRUCT && env_int("CHROM_TILED_WARP", 0) == 0);
   if (!thread_cell) wj = n <= 32 ? 1 : (n <= 64 ? 2 : (n <= 128 ? 4 : 8));
   const int karith = b.arith;
   int T;
   if (wj > 0) T = (karith != CHROM_ARITH_EXACT && wj <= 2) ? 512 : 256;
-  else T = (n <= 8) ? ((karith == CHROM_KARITH_STRUCT || n <= 2) ? 512 : 256) : 256;
+  else T = (n <= 8) ? ((karith == CHROM_KARITH_STRUCT || n <= 2) ? 512 : 256) : 256;  // multi_max_threads
   // widest tile that fits shared memory
   uint32_t tw_max = 0;
   for (uint32_t tw = 8; tw <= b.nz + 1 && tw <= 32u * (uint32_t)T; ++tw) {

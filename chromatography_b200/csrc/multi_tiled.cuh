@@ -707,7 +707,8 @@ __global__ void k_tiled_finalize(const BatchDev b, const unsigned long long* __r
 
 typedef void (*tkern_t)(const BatchDev, double*, const TiledArgs);
 
-// thread per cell (wj == 0) for N = 1..8; warp per cell (wj = 1, 2, 4, 8) in the runtime-n object (N == 0)
+// thread per cell (wj == 0) for N = 1..8 (every mode) and 9..16 (closed form only); warp per cell (wj = 1, 2, 4,
+// 8) in the runtime-n object (N == 0)
 template <int N>
 tkern_t pick_tiled_n(int method, int arith, int wj) {
   if (wj == 0) {
@@ -720,6 +721,10 @@ tkern_t pick_tiled_n(int method, int arith, int wj) {
       if (arith == CHROM_ARITH_EXACT) return k_multi_tiled<N, CHROM_EULER, CHROM_ARITH_EXACT, 0>;
       if (arith == CHROM_KARITH_STRUCT) return k_multi_tiled<N, CHROM_EULER, CHROM_KARITH_STRUCT, 0>;
       return k_multi_tiled<N, CHROM_EULER, CHROM_ARITH_FAST, 0>;
+    } else if constexpr (N >= 9 && N <= 16) {
+      if (arith != CHROM_KARITH_STRUCT) return nullptr;
+      return method == CHROM_RK4 ? k_multi_tiled<N, CHROM_RK4, CHROM_KARITH_STRUCT, 0>
+                                 : k_multi_tiled<N, CHROM_EULER, CHROM_KARITH_STRUCT, 0>;
     }
     return nullptr;
   }

@@ -191,3 +191,22 @@ def test_tiled_plan_reexecute(ctx, monkeypatch):
     assert_bit_equal(a.outlet, b.outlet, "re-executed plan outlet")
     ref = O.solve_multi(to_oracle(m), O.RK4, T, steps, y0=y0)
     assert max_rel_err(a.final_state[0].T, ref.final_state) <= PROFILE_RTOL
+
+
+@pytest.mark.parametrize("n,nz", [(12, 600), (16, 400), (10, 1500)])
+def test_nine_to_sixteen_species_long_columns(ctx, n, nz):
+    """n = 9..16 on columns beyond the register-resident capacity: FAST runs the closed-form elimination one thread
+    per cell on the shared-memory-resident or tiled kernels (EXACT: one warp per cell).  No environment knobs."""
+    steps = 16
+    m, y0, y0_dev = case(n, nz, 31 * n + nz)
+    T = steps * 0.2 * m.dz / m.ue
+    d = describe(ctx, [m], cb.RK4, T, steps, cb.ARITH_FAST)
+    assert ("multi_resident" in d or "thread/cell" in d) and "fast-structured-LU" in d, d
+    ref = O.solve_multi(to_oracle(m), O.RK4, T, steps, y0=y0)
+    f = run_gpu(ctx, [m, m], cb.RK4, T, steps, cb.ARITH_FAST, y0=np.concatenate([y0_dev, y0_dev]))
+    assert not f.status.any()
+    for c in range(2):
+        assert max_rel_err(f.final_state[c].T, ref.final_state) <= PROFILE_RTOL
+        assert max_rel_err(f.outlet[c], ref.outlet) <= PROFILE_RTOL
+    e = run_gpu(ctx, [m], cb.RK4, T, steps, cb.ARITH_EXACT, y0=y0_dev)
+    assert_bit_equal(e.final_state[0].T, ref.final_state, f"n={n} nz={nz} exact")
