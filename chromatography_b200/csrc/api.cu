@@ -414,6 +414,9 @@ int32_t launch_batch(chrom_cuda_ctx* ctx, const BatchDev& b, const LaunchGeom& g
     case 6:
       e = multi_reg_launch(b, g, s);
       break;
+    case 7:
+      e = multi_reg2_launch(b, g, s);
+      break;
     default:
       return fail(ctx, CHROM_ERR_UNSUPPORTED, "plan has no kernel");
   }

@@ -91,6 +91,7 @@ int multi_kernel_arith(int n_species, int arith);
 // multi_reg.cu — LangmuirMulti n <= 16 with the state in registers (FAST arithmetic)
 bool multi_reg_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why);
 cudaError_t multi_reg_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s);
+cudaError_t multi_reg2_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s);  // kind 7 (multi_reg2.cuh)
 
 // multi_tiled.cu — LangmuirMulti beyond the resident capacity (long columns, n > 64): tiles through HBM/L2
 bool multi_tiled_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why);

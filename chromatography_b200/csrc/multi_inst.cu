@@ -1,6 +1,7 @@
 // multi_inst.cu — one translation unit per species count (compiled with -DCHROM_MULTI_N=0..16, 0 = runtime n)
 // so that the nine instantiation sets of multi_kernels.cuh / multi_tiled.cuh build in parallel.
 #include "multi_reg.cuh"
+#include "multi_reg2.cuh"
 #include "multi_tiled.cuh"
 
 #define CHROM_CAT2(a, b) a##b
@@ -21,6 +22,10 @@ int CHROM_CAT(multi_reg_tmax_, CHROM_MULTI_N)(int m) {  // threads per CTA; nega
   const int t = reg_max_threads_rt<CHROM_MULTI_N>(m);
   return reg_acc_shared_rt<CHROM_MULTI_N>(m) ? -t : t;
 }
+#endif
+#if CHROM_MULTI_N > 0 && CHROM_MULTI_N <= 8  // second-generation register-resident kernels: n = 1..8
+rkern_t CHROM_CAT(multi_reg2_pick_, CHROM_MULTI_N)(int method, int variant) { return pick_reg2_n<CHROM_MULTI_N>(method, variant); }
+int CHROM_CAT(multi_reg2_tmax_, CHROM_MULTI_N)(int variant) { return reg2_tmax_rt<CHROM_MULTI_N>(variant); }
 #endif
 #if CHROM_MULTI_N == 0
 void multi_tiled_init_launch(const BatchDev& b, double* ping, unsigned long long* code, cudaStream_t s) {

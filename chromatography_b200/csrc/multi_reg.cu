@@ -14,8 +14,43 @@ typedef void (*rkern_t)(const BatchDev);
 CHROM_DECL(1) CHROM_DECL(2) CHROM_DECL(3) CHROM_DECL(4) CHROM_DECL(5) CHROM_DECL(6) CHROM_DECL(7) CHROM_DECL(8)
 CHROM_DECL(9) CHROM_DECL(10) CHROM_DECL(11) CHROM_DECL(12) CHROM_DECL(13) CHROM_DECL(14) CHROM_DECL(15) CHROM_DECL(16)
 #undef CHROM_DECL
+#define CHROM_DECL2(N)                                   \
+  rkern_t multi_reg2_pick_##N(int method, int variant);  \
+  int multi_reg2_tmax_##N(int variant);
+CHROM_DECL2(1) CHROM_DECL2(2) CHROM_DECL2(3) CHROM_DECL2(4) CHROM_DECL2(5) CHROM_DECL2(6) CHROM_DECL2(7) CHROM_DECL2(8)
+#undef CHROM_DECL2
 
 namespace {
+
+// second-generation kernels (multi_reg2.cuh), n <= 8.  variant: 0 = 1 cell per thread, constants from shared
+// memory; 1 = 1 cell, constants in (uniform) registers; 2 = 2 cells, constants in registers; 3 = 2 cells, shared
+rkern_t lookup_reg2(int n, int method, int variant) {
+  switch (n) {
+    case 1: return multi_reg2_pick_1(method, variant);
+    case 2: return multi_reg2_pick_2(method, variant);
+    case 3: return multi_reg2_pick_3(method, variant);
+    case 4: return multi_reg2_pick_4(method, variant);
+    case 5: return multi_reg2_pick_5(method, variant);
+    case 6: return multi_reg2_pick_6(method, variant);
+    case 7: return multi_reg2_pick_7(method, variant);
+    case 8: return multi_reg2_pick_8(method, variant);
+  }
+  return nullptr;
+}
+
+int tmax_reg2(int n, int variant) {
+  switch (n) {
+    case 1: return multi_reg2_tmax_1(variant);
+    case 2: return multi_reg2_tmax_2(variant);
+    case 3: return multi_reg2_tmax_3(variant);
+    case 4: return multi_reg2_tmax_4(variant);
+    case 5: return multi_reg2_tmax_5(variant);
+    case 6: return multi_reg2_tmax_6(variant);
+    case 7: return multi_reg2_tmax_7(variant);
+    case 8: return multi_reg2_tmax_8(variant);
+  }
+  return 0;
+}
 
 rkern_t lookup_reg(int n, int method, int m) {
   switch (n) {
@@ -63,12 +98,58 @@ int tmax_reg(int n, int m) {
 
 }  // namespace
 
+// Second-generation kernel: chosen when CHROM_REG2 names a variant (experiments) or by default where measured faster.
+static bool multi_reg2_choose(const BatchDev& b, int sm_count, int variant, LaunchGeom* g) {
+  const int n = (int)b.n_species;
+  if (n < 1 || n > 8 || variant < 2 || variant > 8 || variant == 3) return false;
+  const int M = (variant == 5 || variant == 7) ? 1 : 2;
+  const int tmax = tmax_reg2(n, variant);
+  const int T = (int)(((b.nz + M - 1) / M + 31u) / 32u * 32u);
+  if (tmax == 0 || T > tmax) return false;
+  rkern_t k = lookup_reg2(n, b.method, variant);
+  if (!k) return false;
+  // seam ring: 8 slots x warps x (n | 1); dense-fallback scratch: warps x (3 n + n n)
+  const size_t smem = ((size_t)8 * (T / 32) * (n | 1) + (size_t)(T / 32) * (3 * n + n * n)) * sizeof(double);
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, T, smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  g->kind = 7;
+  g->M = M;
+  g->L = T;
+  g->cpw = variant;
+  g->warps_per_col = T / 32;
+  g->block = dim3(T);
+  g->cols_per_wave = (uint32_t)(sm_count * per_sm);
+  g->grid = dim3(std::min<uint32_t>(b.n_cols, g->cols_per_wave));
+  g->smem = smem;
+  char buf[240];
+  snprintf(buf, sizeof buf,
+           "multi_reg2<n=%d,%s,fast-scan-LU,%s> threads/col=%d cells/thread=%d CTAs/SM=%d persistent grid=%u", n,
+           b.method == CHROM_RK4 ? "RK4" : "Euler", variant == 2 ? "unrolled" : (variant <= 5 ? "rolled" : (variant == 6 ? "rolled,free,interleaved" : "rolled,free")), T, M,
+           per_sm, g->grid.x);
+  g->name = buf;
+  return true;
+}
+
+cudaError_t multi_reg2_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s) {
+  rkern_t k = lookup_reg2((int)b.n_species, b.method, g.cpw);
+  if (!k) return cudaErrorInvalidValue;
+  const uint32_t grid = std::min<uint32_t>(b.n_cols, g.cols_per_wave ? g.cols_per_wave : b.n_cols);
+  k<<<dim3(grid), g.block, g.smem, s>>>(b);
+  return cudaGetLastError();
+}
+
 // Cells per thread M in {1, 2, 4}; CHROM_REG_M overrides (experiments).
 bool multi_reg_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::string* why) {
   const int n = (int)b.n_species;
   if (n < 1 || n > 16) {
     if (why) *why = "register-resident multi kernel covers n_species 1..16";
     return false;
+  }
+  if (const char* v2 = getenv("CHROM_REG2")) {
+    if (multi_reg2_choose(b, sm_count, atoi(v2), g)) return true;
   }
   const char* force = getenv("CHROM_REG_M");
   int bestM = 0, bestT = 0;

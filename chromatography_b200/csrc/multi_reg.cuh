@@ -284,9 +284,11 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
     bool maybe = false;  // some cell of this thread may be non-finite after the previous step
     for (uint32_t step = 0; step <= steps; ++step) {
       const int spar = (int)(step & 1u);
-      if (step < steps && tid < N * ST) {  // inlet values of this step: [stage row][species]
-        const int s = tid % N, r = tid / N;
-        inlet[spar][r][s] = tabs[s][(size_t)step * ST + r];
+      if (step < steps) {  // inlet values of this step: [stage row][species]; T may be < N * ST (nz <= 32, n >= 11)
+        for (int i = tid; i < N * ST; i += (int)blockDim.x) {
+          const int s = i % N, r = i / N;
+          inlet[spar][r][s] = tabs[s][(size_t)step * ST + r];
+        }
       }
       // one barrier: publishes the inlet row and carries the previous step's non-finite vote
       const int any_maybe = __syncthreads_or(maybe);

@@ -103,13 +103,14 @@ bool multi_tiled_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::str
   else T = (n <= 8) ? ((karith == CHROM_KARITH_STRUCT || n <= 2) ? 512 : 256) : 256;  // multi_max_threads
   // widest tile that fits shared memory
   uint32_t tw_max = 0;
-  for (uint32_t tw = 8; tw <= b.nz + 1 && tw <= 32u * (uint32_t)T; ++tw) {
+  const uint32_t tw_min = std::min<uint32_t>(8u, b.nz);  // columns shorter than 8 cells are one (narrow) tile
+  for (uint32_t tw = tw_min; tw <= b.nz + 1 && tw <= 32u * (uint32_t)T; ++tw) {
     if (tiled_smem_bytes(n, tw | 1u) > kSmemMax) break;
     tw_max = tw;
   }
   const int cap = env_int("CHROM_TILED_TW", 0);
   if (cap >= 8) tw_max = std::min<uint32_t>(tw_max, (uint32_t)cap);
-  if (tw_max < 8) {
+  if (tw_max < tw_min) {
     if (why) *why = "n_species too large for a shared-memory tile";
     return false;
   }

@@ -286,6 +286,79 @@ void gemv(uint32_t n, const double* a, const double* x, double* y) {
     for (uint32_t i = 0; i < n; ++i) y[i] = a[i + (size_t)j * n] * x[j] + y[i];
 }
 
+// ---- sensitivity variants of the n x n step (tests/test_oracle_sensitivity.py) ------------------------------------
+// nalgebra's source is not in the reference tree, so try_inverse above is a restatement of the published algorithm.
+// These variants replace it by formulations that differ from it in every way a misremembered detail could
+// (reciprocal-multiply vs divide, closed forms vs LU, explicit inverse vs direct solve, f64 vs 80-bit arithmetic):
+// if all of them stay many orders of magnitude inside the 1e-9 contract over full horizons, the unverifiable part of
+// the oracle cannot decide a parity verdict.  0 = the restatement (default).
+//   1  LU inverse for EVERY n (no closed forms), true divisions instead of multiplications by 1/pivot
+//   2  the same in long double (x87 80-bit), rounded to f64 at the end
+//   3  no inverse at all: dv solves A dv = grad by Gaussian elimination with partial pivoting
+int g_inverse_variant = 0;
+
+template <class T>
+bool lu_inverse_generic(uint32_t n, const double* a_in, double* out, bool divide) {
+  std::vector<T> a((size_t)n * n), inv((size_t)n * n, T(0));
+  for (size_t k = 0; k < (size_t)n * n; ++k) a[k] = (T)a_in[k];
+  for (uint32_t i = 0; i < n; ++i) inv[i + (size_t)i * n] = T(1);
+  auto A = [&](uint32_t i, uint32_t j) -> T& { return a[i + (size_t)j * n]; };
+  auto O = [&](uint32_t i, uint32_t j) -> T& { return inv[i + (size_t)j * n]; };
+  for (uint32_t i = 0; i < n; ++i) {
+    uint32_t piv = i;
+    T best = std::fabs(A(i, i));
+    for (uint32_t r = i + 1; r < n; ++r)
+      if (std::fabs(A(r, i)) > best) {
+        best = std::fabs(A(r, i));
+        piv = r;
+      }
+    if (best == T(0)) return false;
+    if (piv != i)
+      for (uint32_t j = 0; j < n; ++j) {
+        std::swap(A(i, j), A(piv, j));
+        std::swap(O(i, j), O(piv, j));
+      }
+    const T d = A(i, i);
+    for (uint32_t r = 0; r < n; ++r) {  // Gauss-Jordan: clear column i in every other row
+      if (r == i) continue;
+      const T m = divide ? A(r, i) / d : A(r, i) * (T(1) / d);
+      for (uint32_t j = 0; j < n; ++j) {
+        A(r, j) -= m * A(i, j);
+        O(r, j) -= m * O(i, j);
+      }
+    }
+  }
+  for (uint32_t i = 0; i < n; ++i)
+    for (uint32_t j = 0; j < n; ++j) out[i + (size_t)j * n] = (double)(O(i, j) / A(i, i));
+  return true;
+}
+
+bool direct_solve(uint32_t n, const double* a_in, const double* b_in, double* x) {
+  std::vector<double> a(a_in, a_in + (size_t)n * n), b(b_in, b_in + n);
+  auto A = [&](uint32_t i, uint32_t j) -> double& { return a[i + (size_t)j * n]; };
+  for (uint32_t i = 0; i < n; ++i) {
+    uint32_t piv = i;
+    for (uint32_t r = i + 1; r < n; ++r)
+      if (std::fabs(A(r, i)) > std::fabs(A(piv, i))) piv = r;
+    if (A(piv, i) == 0.0) return false;
+    if (piv != i) {
+      for (uint32_t j = 0; j < n; ++j) std::swap(A(i, j), A(piv, j));
+      std::swap(b[i], b[piv]);
+    }
+    for (uint32_t r = i + 1; r < n; ++r) {
+      const double m = A(r, i) / A(i, i);
+      for (uint32_t j = i; j < n; ++j) A(r, j) -= m * A(i, j);
+      b[r] -= m * b[i];
+    }
+  }
+  for (uint32_t ii = n; ii-- > 0;) {
+    double t = b[ii];
+    for (uint32_t j = ii + 1; j < n; ++j) t -= A(ii, j) * x[j];
+    x[ii] = t / A(ii, ii);
+  }
+  return true;
+}
+
 struct multi_scratch {
   std::vector<double> c_at_i, jac, mat, inv, grad, dv;
   explicit multi_scratch(uint32_t n)
@@ -301,7 +374,13 @@ void multi_row(const oracle_multi_model& m, uint32_t nz, const double* c, const 
   for (uint32_t j = 0; j < n; ++j)
     for (uint32_t r = 0; r < n; ++r)
       s.mat[r + (size_t)j * n] = ((r == j) ? 1.0 : 0.0) + m.fe * s.jac[r + (size_t)j * n];
-  if (!try_inverse(n, s.mat.data(), s.inv.data())) {  // identity fallback (:790-796)
+  bool inverted;
+  switch (g_inverse_variant) {
+    case 1: inverted = lu_inverse_generic<double>(n, s.mat.data(), s.inv.data(), true); break;
+    case 2: inverted = lu_inverse_generic<long double>(n, s.mat.data(), s.inv.data(), true); break;
+    default: inverted = try_inverse(n, s.mat.data(), s.inv.data()); break;  // 3 decides below
+  }
+  if (!inverted) {  // identity fallback (:790-796)
     for (uint32_t j = 0; j < n; ++j)
       for (uint32_t r = 0; r < n; ++r) s.inv[r + (size_t)j * n] = (r == j) ? 1.0 : 0.0;
     if (n_singular) {
@@ -315,7 +394,8 @@ void multi_row(const oracle_multi_model& m, uint32_t nz, const double* c, const 
     const double c_cur = c[i + (size_t)k * nz];
     s.grad[k] = (i > 0) ? (c_cur - c[(i - 1) + (size_t)k * nz]) / m.dz : (c_cur - inlet[k]) / m.dz;
   }
-  gemv(n, s.inv.data(), s.grad.data(), s.dv.data());
+  if (!(g_inverse_variant == 3 && inverted && direct_solve(n, s.mat.data(), s.grad.data(), s.dv.data())))
+    gemv(n, s.inv.data(), s.grad.data(), s.dv.data());
   for (uint32_t k = 0; k < n; ++k) dc_dt[i + (size_t)k * nz] = (-m.ue) * s.dv[k];
 }
 
@@ -509,6 +589,9 @@ void oracle_solve_multi_batch(const oracle_multi_model* models, uint64_t n_cols,
                                    final_state ? final_state + (size_t)c * nz * n : nullptr, 0, nullptr);
   }
 }
+
+// Sensitivity variants of the n x n step (see g_inverse_variant); 0 restores the restatement.  Process-wide.
+void oracle_set_inverse_variant(int32_t v) { g_inverse_variant = v; }
 
 int32_t oracle_max_threads(void) {
 #ifdef _OPENMP

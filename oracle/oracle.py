@@ -345,6 +345,22 @@ def max_threads() -> int:
     return int(lib().oracle_max_threads())
 
 
+class inverse_variant:
+    """Context manager: run the LangmuirMulti oracle with a sensitivity variant of its n x n step
+    (chrom_oracle.cpp g_inverse_variant: 1 LU inverse with true divisions for every n, 2 the same in long double,
+    3 direct Gaussian-elimination solve without an inverse).  Used by tests/test_oracle_sensitivity.py only."""
+
+    def __init__(self, v: int):
+        self.v = int(v)
+
+    def __enter__(self):
+        lib().oracle_set_inverse_variant(self.v)
+        return self
+
+    def __exit__(self, *a):
+        lib().oracle_set_inverse_variant(0)
+
+
 # --- chromatogram analytics of the reference's validation suite (validation/dissimilarity.rs,
 # validation/main.rs:190-206): test-side helpers, numpy ---------------------------------------
 def trapezoid(times, values):

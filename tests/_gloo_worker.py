@@ -1,6 +1,7 @@
 """Worker of tests/test_dist_gloo.py: one rank of the bench's N>1 path on CPU (gloo).
 The device solve is replaced by the oracle (this is a test of the HOST side of the multi-GPU path:
-per-rank input generation, weak-scaling shard sizes, barrier, max/sum reductions)."""
+per-rank input generation, shard ranges of the strong- and weak-scaling modes, barrier, max/sum reductions).
+GLOO_TEST_SCALING selects the mode; GLOO_TEST_COLS the batch size (strong: in total, weak: per rank)."""
 import hashlib
 import json
 import os
@@ -18,8 +19,10 @@ ranks = bench.Ranks("gloo")
 spec = dict(bench.workload_spec("c3"))
 spec["steps"] = 200          # shortened horizon for the CPU stand-in
 spec["total_time"] = 12.0
-n_cols = 6
-inp = bench.build_inputs(spec, n_cols, ranks.rank)
+scaling = os.environ.get("GLOO_TEST_SCALING", "strong")
+n_total = int(os.environ.get("GLOO_TEST_COLS", "11"))
+inp = bench.build_inputs(spec, ranks.rank, ranks.world, scaling, n_total)
+n_cols = len(inp["cols"])
 cols = np.frombuffer(inp["cols"], dtype=np.float64).reshape(n_cols, 7).copy()
 ranks.barrier()
 t0 = time.perf_counter()
@@ -30,7 +33,7 @@ ms = (time.perf_counter() - t0) * 1e3 + 10.0 * ranks.rank   # make the max-over-
 ranks.barrier()
 units = bench.units_of(spec, n_cols)
 value = bench.aggregate_value(ranks, units, ms)
-out = json.dumps({"rank": ranks.rank, "world": ranks.world, "units": units, "ms": ms, "value": value,
+out = json.dumps({"rank": ranks.rank, "world": ranks.world, "units": units, "n_cols": n_cols, "col0": inp["col0"], "ms": ms, "value": value,
                   "max_ms": ranks.max(ms), "sum_units": ranks.sum(units),
                   "params_sha": hashlib.sha256(cols.tobytes()).hexdigest(),
                   "final_sha": hashlib.sha256(final.tobytes()).hexdigest(), "bad": int(np.count_nonzero(status))})

@@ -280,3 +280,26 @@ def test_randomised_strongly_nonlinear_cases(ctx, seed):
         if ref.status == 0:
             assert max_rel_err(f.final_state[0].T, ref.final_state) <= PROFILE_RTOL, (seed, n, nz, arith)
             assert max_rel_err(f.outlet[0], ref.outlet) <= PROFILE_RTOL, (seed, n, nz, arith)
+
+
+@pytest.mark.parametrize("n", [11, 16])
+@pytest.mark.parametrize("nz", [2, 17, 32])
+def test_short_columns_many_species_inlet_rows(ctx, n, nz):
+    """nz <= 32 with n >= 11: the register-resident kernel runs 32 threads per column while a step's inlet rows
+    hold n * 3 = 33..48 values (RK4) — every row must be loaded (strided load), with a non-zero injection that
+    differs per species so a stale or missing entry cannot go unnoticed."""
+    steps, T = 90, 9.0
+    rng = np.random.default_rng(7000 + 100 * n + nz)
+    species = [cb.SpeciesParams.new(f"S{k}", rng.uniform(0.8, 1.5), rng.uniform(0.1, 0.8), int(rng.integers(1, 4)),
+                                    cb.TemporalInjection.gaussian(2.0 + 0.3 * k, 0.8 + 0.05 * k, 0.02 * (k + 1)))
+               for k in range(n)]
+    m = cb.LangmuirMulti.new(species, nz, 0.4, 1e-3, 0.25 * nz / 100.0)
+    ref = O.solve_multi(to_oracle(m), O.RK4, T, steps)
+    for arith in (cb.ARITH_FAST, cb.ARITH_EXACT):
+        r = run_gpu(ctx, [m], cb.RK4, T, steps, arith)
+        assert r.status[0] == 0
+        if arith == cb.ARITH_EXACT:
+            assert_bit_equal(r.outlet[0], ref.outlet, f"n={n} nz={nz} outlet")
+        else:
+            assert max_rel_err(r.outlet[0], ref.outlet) <= PROFILE_RTOL
+            assert max_rel_err(r.final_state[0].T, ref.final_state) <= PROFILE_RTOL
