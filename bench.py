@@ -512,7 +512,7 @@ def run_workload(ctx, lib, ranks, args, spec, rank, world, local_rank, steps_k, 
     clk = (clocks or {}).get("sm_max_mhz") or measured_peaks().get("sm_max_mhz") or 1965.0
     peak_nominal = 148 * 64 * 2 * clk * 1e6 / 1e12
     # dominant kernel: launches of the solver kernel per execute and its average duration (CUDA events)
-    solver_launches = max(1, int(launches_value / steps_k) - (3 if "single_stream" in desc else 0))
+    solver_launches = max(1, int(launches_value / steps_k) - (4 if "single_stream" in desc else 0))
     launch_ms = (sum(kernel_ms) / steps_k) / solver_launches
     family = desc.split("<")[0]
     traffic, traffic_src = ncu_traffic(family, spec["name"] + ("_dense" if arith_name == "dense" else ""))

@@ -82,6 +82,7 @@ fn solve(ctx: &CudaContext, rk4: bool, scenario: &Scenario, config: &SolverConfi
         method: if rk4 { ffi::CHROM_RK4 } else { ffi::CHROM_EULER }, arith: ffi::CHROM_ARITH_FAST,
         total_time, time_steps: time_steps as u64, n_points: 0, n_species: 1,
         outlet_stride: 0, snapshot_stride: 1,                        // the reference keeps every state (rk4.rs:315)
+        outlet_steps: std::ptr::null(), n_outlet_steps: 0, snapshot_steps: std::ptr::null(), n_snapshot_steps: 0,
     };
     let n_snap = time_steps + 1;
     let mut status = [0i64; 1];
@@ -93,7 +94,7 @@ fn solve(ctx: &CudaContext, rk4: bool, scenario: &Scenario, config: &SolverConfi
         let table = tabulate(&inj, rk4, dt, time_steps);
         let col = ffi::chrom_single_col {
             lambda: f(b, "lambda")?, langmuir_k: f(b, "langmuir_k")?, port_number: f(b, "port_number")?,
-            fe: f(b, "fe")?, ue: f(b, "ue")?, dz: f(b, "dz")?, inj_table: 0, _reserved: 0,
+            fe: f(b, "fe")?, ue: f(b, "ue")?, dz: f(b, "dz")?, inj_table: 0, detector_cell: 0,  // 0 = the column outlet
         };
         let y0: Vec<f64> = initial.get(PhysicalQuantity::Concentration).ok_or("Concentration is required")?
             .as_vector().iter().copied().collect();
@@ -118,7 +119,7 @@ fn solve(ctx: &CudaContext, rk4: bool, scenario: &Scenario, config: &SolverConfi
                 port_number: s["port_number"].as_u64().ok_or("port_number")? as u32, inj_table: k as u32 });
         }
         let col = ffi::chrom_multi_col { fe: f(b, "fe")?, ue: f(b, "ue")?, dz: f(b, "dz")?,
-            stationary_fraction: f(b, "stationary_fraction")?, species_off: 0, _reserved: 0 };
+            stationary_fraction: f(b, "stationary_fraction")?, species_off: 0, detector_cell: 0 };
         // nalgebra DMatrix is column-major nz x n == the device layout [species][nz]
         let y0: Vec<f64> = initial.get(PhysicalQuantity::Concentration).ok_or("Concentration is required")?
             .as_matrix().as_slice().to_vec();

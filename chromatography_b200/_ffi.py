@@ -19,17 +19,18 @@ EULER, RK4 = 0, 1
 ARITH_FAST, ARITH_EXACT, ARITH_FAST_STRUCTURED, ARITH_FAST_DENSE = 0, 1, 3, 4
 INJ_NONE, INJ_DIRAC, INJ_GAUSSIAN, INJ_RECTANGLE = 0, 1, 2, 3
 WANT_OUTLET, WANT_SNAPSHOTS, WANT_FINAL, WANT_SUMMARY, WANT_STATUS = 1, 2, 4, 8, 16
+SUMMARY_LEN = 6  # area, first moment, max, time of max, sigma, min (CHROM_SUMMARY_LEN)
 
 
 class SingleCol(C.Structure):
     _fields_ = [("lambda_", C.c_double), ("langmuir_k", C.c_double), ("port_number", C.c_double),
                 ("fe", C.c_double), ("ue", C.c_double), ("dz", C.c_double),
-                ("inj_table", C.c_uint32), ("_reserved", C.c_uint32)]
+                ("inj_table", C.c_uint32), ("detector_cell", C.c_uint32)]
 
 
 class MultiCol(C.Structure):
     _fields_ = [("fe", C.c_double), ("ue", C.c_double), ("dz", C.c_double), ("stationary_fraction", C.c_double),
-                ("species_off", C.c_uint32), ("_reserved", C.c_uint32)]
+                ("species_off", C.c_uint32), ("detector_cell", C.c_uint32)]
 
 
 class Species(C.Structure):
@@ -40,7 +41,9 @@ class Species(C.Structure):
 class RunCfg(C.Structure):
     _fields_ = [("method", C.c_int32), ("arith", C.c_int32), ("total_time", C.c_double),
                 ("time_steps", C.c_uint64), ("n_points", C.c_uint32), ("n_species", C.c_uint32),
-                ("outlet_stride", C.c_uint64), ("snapshot_stride", C.c_uint64)]
+                ("outlet_stride", C.c_uint64), ("snapshot_stride", C.c_uint64),
+                ("outlet_steps", C.POINTER(C.c_uint64)), ("n_outlet_steps", C.c_uint64),
+                ("snapshot_steps", C.POINTER(C.c_uint64)), ("n_snapshot_steps", C.c_uint64)]
 
 
 class Timing(C.Structure):
@@ -64,6 +67,10 @@ SYMBOLS = {
     "chrom_cuda_bind_host_thread": (C.c_int32, [_vp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "chrom_cuda_validate_cfg": (C.c_char_p, [C.POINTER(RunCfg)]),
     "chrom_cuda_n_samples": (C.c_uint64, [C.c_uint64, C.c_uint64]),
+    "chrom_cuda_cfg_n_out": (C.c_uint64, [C.POINTER(RunCfg)]),
+    "chrom_cuda_cfg_n_snap": (C.c_uint64, [C.POINTER(RunCfg)]),
+    "chrom_cuda_sample_indices": (C.c_uint64, [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64]),
+    "chrom_cuda_node_index": (C.c_uint32, [C.c_double, C.c_double, C.c_uint32]),
     "chrom_cuda_time_points": (None, [C.c_double, C.c_uint64, _dp]),
     "chrom_cuda_table_stages": (C.c_uint32, [C.c_int32]),
     "chrom_cuda_tabulate_injection": (C.c_int32, [C.c_int32, C.c_double, C.c_double, C.c_double, C.c_int32,
@@ -83,6 +90,7 @@ SYMBOLS = {
                                           C.POINTER(_vp)]),
     "chrom_cuda_plan_execute": (C.c_int32, [_vp]),
     "chrom_cuda_plan_download": (C.c_int32, [_vp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int64)]),
+    "chrom_cuda_plan_rsf": (C.c_int32, [_vp, _vp, _dp]),
     "chrom_cuda_plan_describe": (C.c_int32, [_vp, C.c_char_p, C.c_size_t]),
     "chrom_cuda_plan_destroy": (None, [_vp]),
     "chrom_cuda_measure_fp64_peak": (C.c_int32, [_vp, C.c_int32, _dp, _dp]),

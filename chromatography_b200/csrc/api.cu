@@ -34,6 +34,7 @@ struct DeviceState {
   cudaStream_t stream2 = nullptr;      // second compute stream: consecutive chunks of a one-shot solve overlap
   cudaStream_t copy_stream = nullptr;  // device->host copies overlapped with compute (one-shot solves)
   void* flush_buf = nullptr;
+  unsigned long long pool_threshold0 = 0;  // release threshold of the device's default pool before this context raised it
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // h2d0 h2d1 k0 k1 d2h0 d2h1
 };
 
@@ -98,7 +99,8 @@ struct Shard {
   DevBuf<chrom_single_col> scols;
   DevBuf<chrom_multi_col> mcols;
   DevBuf<chrom_species> species;
-  DevBuf<double> tables, y0, outlet, snapshots, final_state, summary, ping, pong, scratch;
+  DevBuf<double> tables, y0, outlet, snapshots, final_state, summary, ping, pong, scratch, series;
+  DevBuf<uint32_t> out_steps, snap_steps;
   DevBuf<long long> status;
   BatchDev b{};
   LaunchGeom g;
@@ -140,10 +142,26 @@ struct chrom_cuda_plan {
   uint64_t n_cols = 0, n_out = 0, n_snap = 0;
   size_t state_len = 0;  // doubles per column state: nz * n_species
   size_t series = 0;     // outlet series per column: n_species
+  std::vector<uint32_t> out_steps, snap_steps;  // explicit sample lists (+ sentinel), empty = strides
   std::vector<std::unique_ptr<Shard>> shards;
   std::string desc;
   double h2d_ms = 0.0;
   uint64_t h2d_bytes = 0;
+  // Whatever path leaves a plan (normal destroy, an error in the middle of a pipelined solve, a failed build): nothing
+  // may still be running on, or copying out of, the buffers the shards are about to free — DevBuf frees on the main
+  // stream only, and host buffers belong to the caller again the moment the call returns.
+  ~chrom_cuda_plan() {
+    if (!ctx) return;
+    for (auto& sh : shards) {
+      if (!sh) continue;
+      DeviceState& d = ctx->devs[sh->dev];
+      cudaSetDevice(d.id);
+      cudaStreamSynchronize(d.stream);
+      cudaStreamSynchronize(d.stream2);
+      cudaStreamSynchronize(d.copy_stream);
+      sh.reset();
+    }
+  }
 };
 
 namespace {
@@ -166,6 +184,21 @@ int32_t check_cfg(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, bool multi) {
     return fail(ctx, CHROM_ERR_UNSUPPORTED, "time_steps >= 2^31 is not supported");
   if (cfg->outlet_stride >= (1ull << 31) || cfg->snapshot_stride >= (1ull << 31))
     return fail(ctx, CHROM_ERR_UNSUPPORTED, "strides >= 2^31 are not supported");
+  const struct {
+    const uint64_t* p;
+    uint64_t n;
+    const char* what;
+  } lists[2] = {{cfg->outlet_steps, cfg->n_outlet_steps, "outlet_steps"}, {cfg->snapshot_steps, cfg->n_snapshot_steps, "snapshot_steps"}};
+  for (const auto& l : lists) {
+    if (!l.p) continue;
+    if (l.n == 0 || l.n > cfg->time_steps + 1)
+      return fail(ctx, CHROM_ERR_INVALID, format("%s: needs 1 .. time_steps + 1 entries, got %llu", l.what, (unsigned long long)l.n));
+    for (uint64_t k = 0; k < l.n; ++k)
+      if (l.p[k] > cfg->time_steps || (k > 0 && l.p[k] <= l.p[k - 1]))
+        return fail(ctx, CHROM_ERR_INVALID,
+                    format("%s[%llu] = %llu: step indices must be strictly increasing and <= time_steps", l.what,
+                           (unsigned long long)k, (unsigned long long)l.p[k]));
+  }
   return CHROM_OK;
 }
 
@@ -221,7 +254,17 @@ int32_t build_shard(chrom_cuda_plan* plan, Shard& sh, const chrom_single_col* sc
   if ((want & CHROM_WANT_OUTLET) && plan->n_out) CUDA_TRY(ctx, sh.outlet.alloc(sh.n_cols * plan->series * plan->n_out, d.stream));
   if ((want & CHROM_WANT_SNAPSHOTS) && plan->n_snap) CUDA_TRY(ctx, sh.snapshots.alloc(sh.n_cols * plan->n_snap * state_len, d.stream));
   if (want & CHROM_WANT_FINAL) CUDA_TRY(ctx, sh.final_state.alloc(sh.n_cols * state_len, d.stream));
-  if (want & CHROM_WANT_SUMMARY) CUDA_TRY(ctx, sh.summary.alloc(sh.n_cols * plan->series * 4, d.stream));
+  if (want & CHROM_WANT_SUMMARY) CUDA_TRY(ctx, sh.summary.alloc(sh.n_cols * plan->series * CHROM_SUMMARY_LEN, d.stream));
+  if (!plan->out_steps.empty() && sh.outlet.p) {
+    CUDA_TRY(ctx, sh.out_steps.alloc(plan->out_steps.size(), d.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(sh.out_steps.p, plan->out_steps.data(), plan->out_steps.size() * sizeof(uint32_t),
+                                  cudaMemcpyHostToDevice, d.stream));
+  }
+  if (!plan->snap_steps.empty() && sh.snapshots.p) {
+    CUDA_TRY(ctx, sh.snap_steps.alloc(plan->snap_steps.size(), d.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(sh.snap_steps.p, plan->snap_steps.data(), plan->snap_steps.size() * sizeof(uint32_t),
+                                  cudaMemcpyHostToDevice, d.stream));
+  }
   CUDA_TRY(ctx, sh.status.alloc(sh.n_cols, d.stream));  // always kept: validate_state is part of the solve
 
   BatchDev& b = sh.b;
@@ -246,6 +289,11 @@ int32_t build_shard(chrom_cuda_plan* plan, Shard& sh, const chrom_single_col* sc
   b.stages = stages;
   b.outlet_stride = sh.outlet.p ? (uint32_t)cfg.outlet_stride : 0u;
   b.snapshot_stride = sh.snapshots.p ? (uint32_t)cfg.snapshot_stride : 0u;
+  b.out_steps = sh.out_steps.p;
+  b.snap_steps = sh.snap_steps.p;
+  b.h_out_steps = sh.out_steps.p ? plan->out_steps.data() : nullptr;
+  b.h_snap_steps = sh.snap_steps.p ? plan->snap_steps.data() : nullptr;
+  b.series = nullptr;
   b.n_out = (uint32_t)plan->n_out;
   b.n_snap = (uint32_t)plan->n_snap;
   b.method = cfg.method;
@@ -262,6 +310,18 @@ int32_t build_shard(chrom_cuda_plan* plan, Shard& sh, const chrom_single_col* sc
     }
     if (worst <= 1e3) b.arith = CHROM_KARITH_POLY;
   }
+  if (!plan->multi && cfg.arith == CHROM_ARITH_FAST) {
+    // The FAST forms fold Cg = -ue/dz into the denominator (A/Cg, B/Cg): a column at rest (ue == 0) or with a
+    // non-finite coefficient would turn a state the reference keeps finite into NaN.  Such a batch runs EXACT.
+    bool safe = true;
+    for (uint64_t c = 0; c < sh.n_cols && safe; ++c) {
+      const chrom_single_col& q = scols[sh.col0 + c];
+      const double cg = -q.ue / q.dz;
+      const double a = (1.0 + q.fe * q.lambda) / cg, bb = q.fe * (q.fe / (1.0 + q.fe) * q.port_number) * q.langmuir_k / cg;
+      safe = (q.ue != 0.0) && std::isfinite(a) && std::isfinite(bb) && std::isfinite(q.langmuir_k);
+    }
+    if (!safe) b.arith = CHROM_ARITH_EXACT;
+  }
   // rk4.rs:238 `dt = total_time / (time_steps as f64)`, :284 `dt / 2.0`, :311 `dt / 6.0`
   b.dt = cfg.total_time / (double)cfg.time_steps;
   b.half_dt = b.dt / 2.0;
@@ -273,9 +333,10 @@ int32_t build_shard(chrom_cuda_plan* plan, Shard& sh, const chrom_single_col* sc
     ok = single_resident_choose(b, d.sm_count, &sh.g, &why);
     if (!ok) ok = single_stream_choose(b, d.sm_count, &sh.g, &why);
     if (ok && sh.g.kind == 3) {
-      if ((want & CHROM_WANT_SUMMARY) && !(sh.outlet.p && cfg.outlet_stride == 1))
-        return fail(ctx, CHROM_ERR_UNSUPPORTED,
-                    "summary on the streaming path (nz > 8192) needs the outlet requested with outlet_stride == 1");
+      if (want & CHROM_WANT_SUMMARY) {  // the summary is formed from a full-rate detector series kept on the device
+        CUDA_TRY(ctx, sh.series.alloc(sh.n_cols * (cfg.time_steps + 1), d.stream));
+        b.series = sh.series.p;
+      }
       CUDA_TRY(ctx, sh.ping.alloc(sh.n_cols * state_len, d.stream));
       CUDA_TRY(ctx, sh.pong.alloc(sh.n_cols * (state_len + single_stream_extra_doubles()), d.stream));  // + status code + coefficients per column
       b.ping = sh.ping.p;
@@ -329,12 +390,19 @@ int32_t make_plan(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, bool multi, con
   if (!inj_tables || n_tables == 0) return fail(ctx, CHROM_ERR_INVALID, "inj_tables is NULL / n_tables == 0");
   const uint32_t n = cfg->n_species;
   if (!multi) {
-    for (uint64_t c = 0; c < n_cols; ++c)
+    for (uint64_t c = 0; c < n_cols; ++c) {
       if (scols[c].inj_table >= n_tables)
         return fail(ctx, CHROM_ERR_INVALID, format("column %llu: inj_table %u >= n_tables %u",
                                                    (unsigned long long)c, scols[c].inj_table, n_tables));
+      if (scols[c].detector_cell > cfg->n_points)
+        return fail(ctx, CHROM_ERR_INVALID, format("column %llu: detector_cell %u exceeds n_points %u (0 = outlet, k = cell k - 1)",
+                                                   (unsigned long long)c, scols[c].detector_cell, cfg->n_points));
+    }
   } else {
     for (uint64_t c = 0; c < n_cols; ++c) {
+      if (mcols[c].detector_cell > cfg->n_points)
+        return fail(ctx, CHROM_ERR_INVALID, format("column %llu: detector_cell %u exceeds n_points %u (0 = outlet, k = cell k - 1)",
+                                                   (unsigned long long)c, mcols[c].detector_cell, cfg->n_points));
       if ((uint64_t)mcols[c].species_off + n > n_species_total)
         return fail(ctx, CHROM_ERR_INVALID, format("column %llu: species range exceeds n_species_total", (unsigned long long)c));
       for (uint32_t k = 0; k < n; ++k)
@@ -349,8 +417,17 @@ int32_t make_plan(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, bool multi, con
   plan->multi = multi;
   plan->want = want;
   plan->n_cols = n_cols;
-  plan->n_out = chrom_cuda_n_samples(cfg->time_steps, cfg->outlet_stride);
-  plan->n_snap = chrom_cuda_n_samples(cfg->time_steps, cfg->snapshot_stride);
+  plan->cfg.outlet_steps = plan->cfg.snapshot_steps = nullptr;  // the caller's lists are copied, never kept
+  plan->n_out = chrom_cuda_cfg_n_out(cfg);
+  plan->n_snap = chrom_cuda_cfg_n_snap(cfg);
+  if (cfg->outlet_steps) {
+    for (uint64_t k = 0; k < cfg->n_outlet_steps; ++k) plan->out_steps.push_back((uint32_t)cfg->outlet_steps[k]);
+    plan->out_steps.push_back(kNoSample);
+  }
+  if (cfg->snapshot_steps) {
+    for (uint64_t k = 0; k < cfg->n_snapshot_steps; ++k) plan->snap_steps.push_back((uint32_t)cfg->snapshot_steps[k]);
+    plan->snap_steps.push_back(kNoSample);
+  }
   plan->state_len = (size_t)cfg->n_points * n;
   plan->series = n;
 
@@ -389,7 +466,7 @@ BatchDev sub_batch(const chrom_cuda_plan* plan, const Shard& sh, uint64_t c0, ui
   if (b.outlet) b.outlet += c0 * ser * plan->n_out;
   if (b.snapshots) b.snapshots += c0 * plan->n_snap * sl;
   if (b.final_state) b.final_state += c0 * sl;
-  if (b.summary) b.summary += c0 * ser * 4;
+  if (b.summary) b.summary += c0 * ser * CHROM_SUMMARY_LEN;
   if (b.status) b.status += c0;
   b.n_cols = (uint32_t)cnt;
   return b;
@@ -428,7 +505,7 @@ int32_t launch_batch(chrom_cuda_ctx* ctx, const BatchDev& b, const LaunchGeom& g
 
 extern "C" {
 
-const char* chrom_cuda_version(void) { return "chrom_cuda 0.1.0 (sm_100a)"; }
+const char* chrom_cuda_version(void) { return "chrom_cuda 0.2.0 (sm_100a)"; }
 
 int32_t chrom_cuda_device_count(void) {
   int n = 0;
@@ -473,7 +550,10 @@ int32_t chrom_cuda_create(const int32_t* device_ids, int32_t n_devices, chrom_cu
     {
       cudaMemPool_t pool;
       CUDA_TRY(nullptr, cudaDeviceGetDefaultMemPool(&pool, id));
-      unsigned long long keep = ~0ull;  // keep freed blocks cached for the next solve
+      // keep freed blocks cached for the next solve; the previous threshold comes back at chrom_cuda_destroy (the
+      // default pool is process-wide: other libraries on the device must not inherit this setting for good)
+      CUDA_TRY(nullptr, cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &d.pool_threshold0));
+      unsigned long long keep = ~0ull;
       CUDA_TRY(nullptr, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
     for (auto& ev : d.ev) CUDA_TRY(nullptr, cudaEventCreate(&ev));
@@ -493,6 +573,11 @@ void chrom_cuda_destroy(chrom_cuda_ctx* ctx) {
     if (d.stream2) cudaStreamDestroy(d.stream2);
     if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
     if (d.flush_buf) cudaFree(d.flush_buf);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, d.id) == cudaSuccess) {
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &d.pool_threshold0);
+      cudaMemPoolTrimTo(pool, 0);  // hand the cached output buffers back
+    }
   }
   delete ctx;
 }
@@ -577,6 +662,47 @@ const char* chrom_cuda_validate_cfg(const chrom_run_cfg* cfg) {
 }
 
 uint64_t chrom_cuda_n_samples(uint64_t time_steps, uint64_t stride) { return stride == 0 ? 0 : time_steps / stride + 1; }
+
+uint64_t chrom_cuda_cfg_n_out(const chrom_run_cfg* cfg) {
+  if (!cfg) return 0;
+  return cfg->outlet_steps ? cfg->n_outlet_steps : chrom_cuda_n_samples(cfg->time_steps, cfg->outlet_stride);
+}
+
+uint64_t chrom_cuda_cfg_n_snap(const chrom_run_cfg* cfg) {
+  if (!cfg) return 0;
+  return cfg->snapshot_steps ? cfg->n_snapshot_steps : chrom_cuda_n_samples(cfg->time_steps, cfg->snapshot_stride);
+}
+
+// sample_indices — src/physics/traits.rs:1010-1023 (integer division, last index forced to total - 1)
+uint64_t chrom_cuda_sample_indices(uint64_t total, uint64_t n, uint64_t* out, uint64_t cap) {
+  auto put = [&](uint64_t k, uint64_t v) {
+    if (out && k < cap) out[k] = v;
+  };
+  if (n == 0 || n >= total) {
+    for (uint64_t i = 0; i < total; ++i) put(i, i);
+    return total;
+  }
+  if (n == 1) {
+    put(0, 0);
+    return 1;
+  }
+  for (uint64_t i = 0; i < n; ++i) put(i, (i * (total - 1)) / (n - 1));
+  put(n - 1, total - 1);
+  return n;
+}
+
+// Detector::node_index — src/domain/detector.rs:285-290: `(z / dz).round() as usize` (round half away from zero,
+// saturating cast), `min(n_points - 1)`
+uint32_t chrom_cuda_node_index(double position, double column_length, uint32_t n_points) {
+  if (n_points == 0) return 0;
+  const double dz = column_length / (double)n_points;
+  const double r = std::round(position / dz);
+  uint64_t idx = 0;
+  if (r != r || r <= 0.0) idx = 0;  // NaN and negatives saturate to 0 in a Rust `as usize`
+  else if (r >= 1.8446744073709552e19) idx = ~0ull;
+  else idx = (uint64_t)r;
+  return (uint32_t)std::min<uint64_t>(idx, (uint64_t)n_points - 1);
+}
 
 void chrom_cuda_time_points(double total_time, uint64_t time_steps, double* out) {
   const double dt = total_time / (double)time_steps;
@@ -717,7 +843,7 @@ int32_t chrom_cuda_plan_download(chrom_cuda_plan* plan, double* outlet, double* 
     CUDA_TRY(ctx, copy(*sh, d.stream, outlet, sh->outlet.p, plan->series * plan->n_out * sizeof(double)));
     CUDA_TRY(ctx, copy(*sh, d.stream, snapshots, sh->snapshots.p, plan->n_snap * plan->state_len * sizeof(double)));
     CUDA_TRY(ctx, copy(*sh, d.stream, final_state, sh->final_state.p, plan->state_len * sizeof(double)));
-    CUDA_TRY(ctx, copy(*sh, d.stream, summary, sh->summary.p, plan->series * 4 * sizeof(double)));
+    CUDA_TRY(ctx, copy(*sh, d.stream, summary, sh->summary.p, plan->series * CHROM_SUMMARY_LEN * sizeof(double)));
     CUDA_TRY(ctx, copy(*sh, d.stream, status, sh->status.p, sizeof(long long)));
   }
   for (auto& sh : plan->shards) {
@@ -730,20 +856,47 @@ int32_t chrom_cuda_plan_download(chrom_cuda_plan* plan, double* outlet, double* 
   return CHROM_OK;
 }
 
+int32_t chrom_cuda_plan_rsf(chrom_cuda_plan* a, chrom_cuda_plan* b, double* rsf) {
+  if (!a || !b || !rsf) return CHROM_ERR_INVALID;
+  chrom_cuda_ctx* ctx = a->ctx;
+  if (b->ctx != ctx) return fail(ctx, CHROM_ERR_INVALID, "plan_rsf: the two plans belong to different contexts");
+  if (a->n_cols != b->n_cols || a->series != b->series || a->n_out != b->n_out || a->shards.size() != b->shards.size() ||
+      a->cfg.total_time != b->cfg.total_time || a->cfg.time_steps != b->cfg.time_steps ||
+      a->cfg.outlet_stride != b->cfg.outlet_stride || a->out_steps != b->out_steps)
+    return fail(ctx, CHROM_ERR_INVALID,
+                "plan_rsf: the two plans must hold the same columns, species and outlet sampling (one time grid)");
+  if (a->n_out < 2) return fail(ctx, CHROM_ERR_INVALID, "plan_rsf: needs at least two outlet samples");
+  const double dt = a->cfg.total_time / (double)a->cfg.time_steps;
+  std::vector<DevBuf<double>> out(a->shards.size());
+  for (size_t si = 0; si < a->shards.size(); ++si) {
+    Shard& sa = *a->shards[si];
+    Shard& sb = *b->shards[si];
+    if (!sa.outlet.p || !sb.outlet.p)
+      return fail(ctx, CHROM_ERR_INVALID, "plan_rsf: both plans must have been built with CHROM_WANT_OUTLET");
+    DeviceState& d = ctx->devs[sa.dev];
+    CUDA_TRY(ctx, cudaSetDevice(d.id));
+    const size_t n_series = sa.n_cols * a->series;
+    CUDA_TRY(ctx, out[si].alloc(n_series, d.stream));
+    CUDA_TRY(ctx, rsf_launch(sa.outlet.p, sb.outlet.p, n_series, (uint32_t)a->n_out, sa.out_steps.p,
+                             (uint32_t)a->cfg.outlet_stride, dt, out[si].p, d.stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(rsf + sa.col0 * a->series, out[si].p, n_series * sizeof(double), cudaMemcpyDeviceToHost,
+                                  d.stream));
+  }
+  for (auto& sh : a->shards) {
+    DeviceState& d = ctx->devs[sh->dev];
+    CUDA_TRY(ctx, cudaSetDevice(d.id));
+    CUDA_TRY(ctx, cudaStreamSynchronize(d.stream));
+  }
+  return CHROM_OK;
+}
+
 int32_t chrom_cuda_plan_describe(const chrom_cuda_plan* plan, char* buf, size_t buf_len) {
   if (!plan || !buf || buf_len == 0) return CHROM_ERR_INVALID;
   snprintf(buf, buf_len, "%s", plan->desc.c_str());
   return CHROM_OK;
 }
 
-void chrom_cuda_plan_destroy(chrom_cuda_plan* plan) {
-  if (!plan) return;
-  for (auto& sh : plan->shards) {
-    cudaSetDevice(plan->ctx->devs[sh->dev].id);
-    sh.reset();
-  }
-  delete plan;
-}
+void chrom_cuda_plan_destroy(chrom_cuda_plan* plan) { delete plan; }  // ~chrom_cuda_plan drains the streams first
 
 // ---- one-shot solves --------------------------------------------------------------------------
 
@@ -754,11 +907,15 @@ static int32_t solve_pipelined(chrom_cuda_ctx* ctx, chrom_cuda_plan* plan, doubl
                                double* final_state, double* summary, int64_t* status) {
   const size_t sl = plan->state_len, ser = plan->series;
   const size_t per_col = (outlet ? ser * plan->n_out : 0) + (snapshots ? plan->n_snap * sl : 0) +
-                         (final_state ? sl : 0) + (summary ? ser * 4 : 0);
+                         (final_state ? sl : 0) + (summary ? ser * CHROM_SUMMARY_LEN : 0);
   bool worth = false;
-  for (auto& sh : plan->shards)
-    worth |= sh->g.cols_per_wave > 0 && sh->g.kind != 3 && sh->n_cols >= 2ull * sh->g.cols_per_wave &&
-             sh->n_cols * per_col * sizeof(double) >= ((size_t)64 << 20);
+  for (auto& sh : plan->shards) {
+    const bool big = sh->n_cols * per_col * sizeof(double) >= ((size_t)64 << 20);
+    // several waves of columns: chunks;  a register-resident single-species batch of any size: its (only) chunk is
+    // advanced in time slices, the outlet samples of a slice going back while the next one computes
+    worth |= big && sh->g.cols_per_wave > 0 && sh->g.kind != 3 && sh->n_cols >= 2ull * sh->g.cols_per_wave;
+    worth |= big && (sh->g.kind == 1 || sh->g.kind == 2) && outlet && final_state && !snapshots && plan->out_steps.empty();
+  }
   if (!worth) return 1;
   const double t0 = now_ms();
   uint64_t launches = 0, bytes = 0;
@@ -783,8 +940,8 @@ static int32_t solve_pipelined(chrom_cuda_ctx* ctx, chrom_cuda_plan* plan, doubl
       if (next[si] >= sh.n_cols) continue;
       DeviceState& d = ctx->devs[sh.dev];
       CUDA_TRY(ctx, cudaSetDevice(d.id));
-      const uint64_t waves = (sh.n_cols + sh.g.cols_per_wave - 1) / sh.g.cols_per_wave;
-      const uint64_t chunk = (uint64_t)sh.g.cols_per_wave * std::max<uint64_t>(1, (waves + 7) / 8);
+      const uint64_t waves = sh.g.cols_per_wave ? (sh.n_cols + sh.g.cols_per_wave - 1) / sh.g.cols_per_wave : 1;
+      const uint64_t chunk = std::max<uint64_t>(1, (uint64_t)sh.g.cols_per_wave * std::max<uint64_t>(1, (waves + 7) / 8));
       const uint64_t c0 = next[si], cnt = std::min<uint64_t>(chunk, sh.n_cols - c0);
       next[si] = c0 + cnt;
       more |= next[si] < sh.n_cols;
@@ -796,9 +953,10 @@ static int32_t solve_pipelined(chrom_cuda_ctx* ctx, chrom_cuda_plan* plan, doubl
       // The copy of the LAST chunk is the one nothing overlaps.  Where the kernel can continue from a carried
       // state (register-resident single-species kernels, no on-device summary, no snapshots), that chunk is
       // advanced in kSlices time slices and the outlet samples of a slice go back while the next one computes.
-      constexpr uint32_t kSlices = 4;
       const bool last_chunk = next[si] >= sh.n_cols;
-      if (last_chunk && (sh.g.kind == 1 || sh.g.kind == 2) && !summary && !snapshots && outlet && b.outlet &&
+      // (a batch that is one chunk has nothing else to hide its copy behind: more, shorter slices)
+      const uint32_t kSlices = (c0 == 0 && last_chunk) ? 8u : 4u;
+      if (last_chunk && (sh.g.kind == 1 || sh.g.kind == 2) && !snapshots && outlet && b.outlet && !b.out_steps &&
           b.final_state && b.outlet_stride > 0 && b.steps >= 64u * kSlices) {
         const size_t n_out = plan->n_out;
         for (uint32_t k = 0; k < kSlices && rc == CHROM_OK; ++k) {
@@ -834,6 +992,11 @@ static int32_t solve_pipelined(chrom_cuda_ctx* ctx, chrom_cuda_plan* plan, doubl
                                         d.copy_stream));
           bytes += cnt * sizeof(long long);
         }
+        if (summary && b.summary) {  // finished by the last slice (the earlier ones parked their raw sums there)
+          CUDA_TRY(ctx, cudaMemcpyAsync(summary + (sh.col0 + c0) * ser * CHROM_SUMMARY_LEN, b.summary,
+                                        cnt * ser * CHROM_SUMMARY_LEN * sizeof(double), cudaMemcpyDeviceToHost, d.copy_stream));
+          bytes += cnt * ser * CHROM_SUMMARY_LEN * sizeof(double);
+        }
         continue;
       }
       rc = launch_batch(ctx, b, sh.g, cs);
@@ -853,7 +1016,7 @@ static int32_t solve_pipelined(chrom_cuda_ctx* ctx, chrom_cuda_plan* plan, doubl
       CUDA_TRY(ctx, copy(outlet, b.outlet, ser * plan->n_out * sizeof(double)));
       CUDA_TRY(ctx, copy(snapshots, b.snapshots, plan->n_snap * sl * sizeof(double)));
       CUDA_TRY(ctx, copy(final_state, b.final_state, sl * sizeof(double)));
-      CUDA_TRY(ctx, copy(summary, b.summary, ser * 4 * sizeof(double)));
+      CUDA_TRY(ctx, copy(summary, b.summary, ser * CHROM_SUMMARY_LEN * sizeof(double)));
       CUDA_TRY(ctx, copy(status, b.status, sizeof(long long)));
     }
   }
@@ -899,8 +1062,8 @@ static int32_t solve_common(chrom_cuda_ctx* ctx, chrom_cuda_plan* plan, double* 
 static uint32_t want_mask(const chrom_run_cfg* cfg, const double* outlet, const double* snapshots,
                           const double* final_state, const double* summary) {
   uint32_t w = CHROM_WANT_STATUS;
-  if (outlet && cfg && cfg->outlet_stride) w |= CHROM_WANT_OUTLET;
-  if (snapshots && cfg && cfg->snapshot_stride) w |= CHROM_WANT_SNAPSHOTS;
+  if (outlet && cfg && (cfg->outlet_stride || cfg->outlet_steps)) w |= CHROM_WANT_OUTLET;
+  if (snapshots && cfg && (cfg->snapshot_stride || cfg->snapshot_steps)) w |= CHROM_WANT_SNAPSHOTS;
   if (final_state) w |= CHROM_WANT_FINAL;
   if (summary) w |= CHROM_WANT_SUMMARY;
   return w;

@@ -6,6 +6,7 @@
 #include <string>
 
 #include "../../include/chrom_cuda.h"
+#include "sampling.cuh"
 
 namespace chrom {
 
@@ -41,6 +42,11 @@ struct BatchDev {
                                   // kernels only: a one-shot solve time-slices its last chunk; y0 = the carried state)
   uint32_t stages;  // table entries per step
   uint32_t outlet_stride, snapshot_stride;
+  const uint32_t* out_steps;   // explicit outlet sample list (device, kNoSample-terminated) or null = the stride
+  const uint32_t* snap_steps;  // explicit snapshot list or null
+  const uint32_t* h_out_steps;   // host copies of the two lists (the streaming path schedules samples on the host)
+  const uint32_t* h_snap_steps;
+  double* series;  // streaming path with a summary: full-rate detector series [n_cols][steps + 1] (device scratch)
   uint32_t n_out, n_snap;
   int32_t method, arith;
   double dt, half_dt, sixth_dt;  // dt, dt/2.0, dt/6.0 evaluated on the host in IEEE double
@@ -68,6 +74,10 @@ struct LaunchGeom {
   size_t smem = 0;
   uint64_t launches_per_execute = 1;
   uint32_t cols_per_wave = 0;  // columns one full wave of CTAs covers (0: the path is not chunkable)
+  // single_resident, batch that cannot fill the machine: the columns beyond `cols_first` run as a SECOND launch with
+  // its own cells per lane on a second stream, so that every SM sub-partition carries one warp of each (M2 = 0: off)
+  int M2 = 0, L2 = 0, cpw2 = 0;
+  uint32_t cols_first = 0;
   // multi_tiled: tile width, halo, shared-memory pitch, steps per launch, species per lane (0 = thread per cell)
   uint32_t tw = 0, halo = 0, pitch = 0, nsub = 0;
   int wj = 0;
@@ -98,6 +108,10 @@ bool multi_tiled_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::str
 cudaError_t multi_tiled_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s);
 size_t multi_tiled_extra_doubles(uint32_t n_species);  // per column, behind the pong buffer: status code + summary
 size_t multi_tiled_scratch_doubles(const BatchDev& b, const LaunchGeom& g);
+
+// analytics.cu — surface resolution Rsf between two device-resident outlet series on one time grid
+cudaError_t rsf_launch(const double* a, const double* b, size_t n_series, uint32_t n_out, const uint32_t* steps_list,
+                       uint32_t stride, double dt, double* out, cudaStream_t s);
 
 // probe.cu
 cudaError_t measure_fp64_peak(int sm_count, cudaStream_t s, double* tflops, double* ms);

@@ -24,8 +24,8 @@ int CHROM_CAT(multi_reg_tmax_, CHROM_MULTI_N)(int m) {  // threads per CTA; nega
 }
 #endif
 #if CHROM_MULTI_N > 0 && CHROM_MULTI_N <= 8  // second-generation register-resident kernels: n = 1..8
-rkern_t CHROM_CAT(multi_reg2_pick_, CHROM_MULTI_N)(int method, int variant) { return pick_reg2_n<CHROM_MULTI_N>(method, variant); }
-int CHROM_CAT(multi_reg2_tmax_, CHROM_MULTI_N)(int variant) { return reg2_tmax_rt<CHROM_MULTI_N>(variant); }
+rkern_t CHROM_CAT(multi_reg2_pick_, CHROM_MULTI_N)(int method) { return pick_reg2_n<CHROM_MULTI_N>(method); }
+int CHROM_CAT(multi_reg2_tmax_, CHROM_MULTI_N)() { return reg2_tmax_rt<CHROM_MULTI_N>(); }
 #endif
 #if CHROM_MULTI_N == 0
 void multi_tiled_init_launch(const BatchDev& b, double* ping, unsigned long long* code, cudaStream_t s) {

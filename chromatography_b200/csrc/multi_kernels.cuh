@@ -563,8 +563,8 @@ __global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_reside
   double* U0 = ACC + plane;
   double* U1 = U0 + plane;
   double* inlet = U1 + plane;                        // [3][n] current step's inlet values
-  double* summ = inlet + 3 * n;                      // [n][5]: area, moment, max, tmax, v_prev
-  SpeciesConst* sc = (SpeciesConst*)(summ + 5 * n);  // [n]
+  double* summ = inlet + 3 * n;                               // [n] Summ (kSummSlots doubles each)
+  SpeciesConst* sc = (SpeciesConst*)(summ + kSummSlots * n);  // [n]
   __shared__ const double* tabs[CAP];
 
   const double dt = b.dt, h2 = b.half_dt, h6 = b.sixth_dt;
@@ -601,18 +601,18 @@ __global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_reside
     __syncthreads();
 
     // initial samples
+    const uint32_t det = detector_of(cp.detector_cell, nz);  // where outlet and summary are sampled
     for (int s = tid; s < n; s += T) {
-      const double v0 = Y[(size_t)s * nz + nz - 1];
-      if (b.outlet) b.outlet[((size_t)col * n + s) * b.n_out] = v0;
-      summ[s * 5 + 0] = 0.0;
-      summ[s * 5 + 1] = 0.0;
-      summ[s * 5 + 2] = v0;
-      summ[s * 5 + 3] = 0.0;
-      summ[s * 5 + 4] = v0;
+      const double v0 = Y[(size_t)s * nz + det];
+      if (b.outlet && sample_has_initial(b.out_steps, b.outlet_stride)) b.outlet[((size_t)col * n + s) * b.n_out] = v0;
+      summ_init(reinterpret_cast<Summ*>(summ)[s], v0);
     }
-    if (b.snapshots)
+    if (b.snapshots && sample_has_initial(b.snap_steps, b.snapshot_stride))
       for (size_t i = tid; i < plane; i += T) b.snapshots[(size_t)col * b.n_snap * plane + i] = Y[i];
-    uint32_t out_count = b.outlet_stride, snap_count = b.snapshot_stride, out_slot = 1, snap_slot = 1;
+    SampleCursor oc = sample_begin(b.out_steps, b.n_out, b.outlet ? b.outlet_stride : 0u, 0u);
+    SampleCursor sc_ = sample_begin(b.snap_steps, b.n_snap, b.snapshots ? b.snapshot_stride : 0u, 0u);
+    if (!b.outlet) oc.next = kNoSample;
+    if (!b.snapshots) sc_.next = kNoSample;
     bool done = false;
 
     // One stage: K = f(SRC, inlet row `irow`), then the stage algebra selected by `stage`.
@@ -690,30 +690,18 @@ __global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_reside
       const int any_bad = __syncthreads_or(bad);
 
       // ---- samples --------------------------------------------------------------------------
-      const bool out_now = b.outlet && (--out_count == 0);
-      if (out_now) out_count = b.outlet_stride;
-      for (int s = tid; s < n; s += T) {
-        const double v = Y[(size_t)s * nz + nz - 1];
-        if (out_now) b.outlet[((size_t)col * n + s) * b.n_out + out_slot] = v;
-        if (b.summary) {
-          const double t0 = (double)step * dt, t1 = ((double)step + 1.0) * dt;
-          const double w = 0.5 * (t1 - t0);
-          double* sm = summ + s * 5;
-          sm[0] = fma(w, sm[4] + v, sm[0]);
-          sm[1] = fma(w, fma(t0, sm[4], t1 * v), sm[1]);
-          if (v > sm[2]) {
-            sm[2] = v;
-            sm[3] = t1;
-          }
-          sm[4] = v;
+      const bool out_now = (step + 1u == oc.next);
+      if (out_now || b.summary)
+        for (int s = tid; s < n; s += T) {
+          const double v = Y[(size_t)s * nz + det];
+          if (out_now) b.outlet[((size_t)col * n + s) * b.n_out + oc.k] = v;
+          if (b.summary) summ_step(reinterpret_cast<Summ*>(summ)[s], v, step, dt);
         }
-      }
-      if (out_now) ++out_slot;
-      if (b.snapshots && --snap_count == 0) {
-        snap_count = b.snapshot_stride;
-        double* dst = b.snapshots + ((size_t)col * b.n_snap + snap_slot) * plane;
+      if (out_now) sample_advance(oc, b.out_steps, b.outlet_stride);
+      if (step + 1u == sc_.next) {
+        double* dst = b.snapshots + ((size_t)col * b.n_snap + sc_.k) * plane;
         for (size_t i = tid; i < plane; i += T) dst[i] = Y[i];
-        ++snap_slot;
+        sample_advance(sc_, b.snap_steps, b.snapshot_stride);
       }
       if (any_bad && !done) {  // validate_state: NaN anywhere wins over Inf (solver/mod.rs:519-548)
         bool has_nan = false;
@@ -727,14 +715,8 @@ __global__ void __launch_bounds__(multi_max_threads(N, ARITH), 1) k_multi_reside
     if (b.final_state)
       for (size_t i = tid; i < plane; i += T) b.final_state[(size_t)col * plane + i] = Y[i];
     if (b.summary)
-      for (int s = tid; s < n; s += T) {
-        double* o = b.summary + ((size_t)col * n + s) * 4;
-        const double* sm = summ + s * 5;
-        o[0] = sm[0];
-        o[1] = (sm[0] != 0.0) ? sm[1] / sm[0] : 0.0;
-        o[2] = sm[2];
-        o[3] = sm[3];
-      }
+      for (int s = tid; s < n; s += T)
+        summ_store(b.summary + ((size_t)col * n + s) * CHROM_SUMMARY_LEN, reinterpret_cast<const Summ*>(summ)[s]);
   }
 }
 

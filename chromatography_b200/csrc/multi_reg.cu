@@ -14,40 +14,39 @@ typedef void (*rkern_t)(const BatchDev);
 CHROM_DECL(1) CHROM_DECL(2) CHROM_DECL(3) CHROM_DECL(4) CHROM_DECL(5) CHROM_DECL(6) CHROM_DECL(7) CHROM_DECL(8)
 CHROM_DECL(9) CHROM_DECL(10) CHROM_DECL(11) CHROM_DECL(12) CHROM_DECL(13) CHROM_DECL(14) CHROM_DECL(15) CHROM_DECL(16)
 #undef CHROM_DECL
-#define CHROM_DECL2(N)                                   \
-  rkern_t multi_reg2_pick_##N(int method, int variant);  \
-  int multi_reg2_tmax_##N(int variant);
+#define CHROM_DECL2(N)                      \
+  rkern_t multi_reg2_pick_##N(int method);  \
+  int multi_reg2_tmax_##N();
 CHROM_DECL2(1) CHROM_DECL2(2) CHROM_DECL2(3) CHROM_DECL2(4) CHROM_DECL2(5) CHROM_DECL2(6) CHROM_DECL2(7) CHROM_DECL2(8)
 #undef CHROM_DECL2
 
 namespace {
 
-// second-generation kernels (multi_reg2.cuh), n <= 8.  variant: 0 = 1 cell per thread, constants from shared
-// memory; 1 = 1 cell, constants in (uniform) registers; 2 = 2 cells, constants in registers; 3 = 2 cells, shared
-rkern_t lookup_reg2(int n, int method, int variant) {
+// second-generation kernels (multi_reg2.cuh), n <= 8: 2 cells per thread
+rkern_t lookup_reg2(int n, int method) {
   switch (n) {
-    case 1: return multi_reg2_pick_1(method, variant);
-    case 2: return multi_reg2_pick_2(method, variant);
-    case 3: return multi_reg2_pick_3(method, variant);
-    case 4: return multi_reg2_pick_4(method, variant);
-    case 5: return multi_reg2_pick_5(method, variant);
-    case 6: return multi_reg2_pick_6(method, variant);
-    case 7: return multi_reg2_pick_7(method, variant);
-    case 8: return multi_reg2_pick_8(method, variant);
+    case 1: return multi_reg2_pick_1(method);
+    case 2: return multi_reg2_pick_2(method);
+    case 3: return multi_reg2_pick_3(method);
+    case 4: return multi_reg2_pick_4(method);
+    case 5: return multi_reg2_pick_5(method);
+    case 6: return multi_reg2_pick_6(method);
+    case 7: return multi_reg2_pick_7(method);
+    case 8: return multi_reg2_pick_8(method);
   }
   return nullptr;
 }
 
-int tmax_reg2(int n, int variant) {
+int tmax_reg2(int n) {
   switch (n) {
-    case 1: return multi_reg2_tmax_1(variant);
-    case 2: return multi_reg2_tmax_2(variant);
-    case 3: return multi_reg2_tmax_3(variant);
-    case 4: return multi_reg2_tmax_4(variant);
-    case 5: return multi_reg2_tmax_5(variant);
-    case 6: return multi_reg2_tmax_6(variant);
-    case 7: return multi_reg2_tmax_7(variant);
-    case 8: return multi_reg2_tmax_8(variant);
+    case 1: return multi_reg2_tmax_1();
+    case 2: return multi_reg2_tmax_2();
+    case 3: return multi_reg2_tmax_3();
+    case 4: return multi_reg2_tmax_4();
+    case 5: return multi_reg2_tmax_5();
+    case 6: return multi_reg2_tmax_6();
+    case 7: return multi_reg2_tmax_7();
+    case 8: return multi_reg2_tmax_8();
   }
   return 0;
 }
@@ -98,15 +97,17 @@ int tmax_reg(int n, int m) {
 
 }  // namespace
 
+constexpr int kReg2MinSpecies = 5;
+
 // Second-generation kernel: chosen when CHROM_REG2 names a variant (experiments) or by default where measured faster.
-static bool multi_reg2_choose(const BatchDev& b, int sm_count, int variant, LaunchGeom* g) {
+static bool multi_reg2_choose(const BatchDev& b, int sm_count, LaunchGeom* g) {
   const int n = (int)b.n_species;
-  if (n < 1 || n > 8 || variant < 2 || variant > 8 || variant == 3) return false;
-  const int M = (variant == 5 || variant == 7) ? 1 : 2;
-  const int tmax = tmax_reg2(n, variant);
+  if (n < 1 || n > 8) return false;
+  const int M = 2;
+  const int tmax = tmax_reg2(n);
   const int T = (int)(((b.nz + M - 1) / M + 31u) / 32u * 32u);
   if (tmax == 0 || T > tmax) return false;
-  rkern_t k = lookup_reg2(n, b.method, variant);
+  rkern_t k = lookup_reg2(n, b.method);
   if (!k) return false;
   // seam ring: 8 slots x warps x (n | 1); dense-fallback scratch: warps x (3 n + n n)
   const size_t smem = ((size_t)8 * (T / 32) * (n | 1) + (size_t)(T / 32) * (3 * n + n * n)) * sizeof(double);
@@ -118,7 +119,7 @@ static bool multi_reg2_choose(const BatchDev& b, int sm_count, int variant, Laun
   g->kind = 7;
   g->M = M;
   g->L = T;
-  g->cpw = variant;
+  g->cpw = 1;
   g->warps_per_col = T / 32;
   g->block = dim3(T);
   g->cols_per_wave = (uint32_t)(sm_count * per_sm);
@@ -126,15 +127,15 @@ static bool multi_reg2_choose(const BatchDev& b, int sm_count, int variant, Laun
   g->smem = smem;
   char buf[240];
   snprintf(buf, sizeof buf,
-           "multi_reg2<n=%d,%s,fast-scan-LU,%s> threads/col=%d cells/thread=%d CTAs/SM=%d persistent grid=%u", n,
-           b.method == CHROM_RK4 ? "RK4" : "Euler", variant == 2 ? "unrolled" : (variant <= 5 ? "rolled" : (variant == 6 ? "rolled,free,interleaved" : "rolled,free")), T, M,
+           "multi_reg2<n=%d,%s,fast-scan-LU> threads/col=%d cells/thread=%d CTAs/SM=%d persistent grid=%u", n,
+           b.method == CHROM_RK4 ? "RK4" : "Euler", T, M,
            per_sm, g->grid.x);
   g->name = buf;
   return true;
 }
 
 cudaError_t multi_reg2_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s) {
-  rkern_t k = lookup_reg2((int)b.n_species, b.method, g.cpw);
+  rkern_t k = lookup_reg2((int)b.n_species, b.method);
   if (!k) return cudaErrorInvalidValue;
   const uint32_t grid = std::min<uint32_t>(b.n_cols, g.cols_per_wave ? g.cols_per_wave : b.n_cols);
   k<<<dim3(grid), g.block, g.smem, s>>>(b);
@@ -148,8 +149,14 @@ bool multi_reg_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::strin
     if (why) *why = "register-resident multi kernel covers n_species 1..16";
     return false;
   }
-  if (const char* v2 = getenv("CHROM_REG2")) {
-    if (multi_reg2_choose(b, sm_count, atoi(v2), g)) return true;
+  // Second generation (multi_reg2.cuh) where it measured faster on B200 (profiles/r2_multi_shapes.jsonl): n >= 5
+  // (C5 645 -> 471 ms, n = 7 nz = 200 141 -> 103 ms, n = 6 nz = 256 107 -> 81 ms, n = 5 nz = 300 108 -> 94 ms); n <= 4
+  // stays with the first generation (2 or 4 cells per thread, shared-memory exchange: 1.84e11 vs 1.71e11 cell-stage/s
+  // at n = 2).  CHROM_REG2 = 0 forces the first generation, 2 the second (experiments).
+  {
+    const char* v2 = getenv("CHROM_REG2");
+    const bool second = v2 ? atoi(v2) != 0 : n >= kReg2MinSpecies;
+    if (second && multi_reg2_choose(b, sm_count, g)) return true;
   }
   const char* force = getenv("CHROM_REG_M");
   int bestM = 0, bestT = 0;

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
   constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
   __shared__ SpeciesConst sc[N];
   __shared__ double inlet[2][3][N];   // [step parity][stage row][species]
-  __shared__ double summ[N][5];       // area, moment, max, tmax, previous sample (outlet owner only)
+  __shared__ Summ summ[N];            // running summary of the detector signal (detector owner only)
   __shared__ const double* tabs[N];
   __shared__ double colc[2];          // max_i K_i, min_i (1 + fe lambda_i) of the current column
   constexpr bool ACC_SH = reg_acc_shared(N, M);
@@ -136,8 +136,6 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
   const uint32_t nz = b.nz;
   const int cell0 = tid * M;
   const int nv = max(0, min(M, (int)nz - cell0));  // real cells of this thread
-  const int t_out = (int)(nz - 1) / M, j_out = (int)(nz - 1) - t_out * M;
-  const bool out_thread = (tid == t_out);
   const double dt = b.dt, h2 = b.half_dt, h6 = b.sixth_dt;
   const uint32_t steps = b.steps;
 
@@ -146,6 +144,9 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
     const double fe = cp.fe;
     const double cg = -cp.ue / cp.dz;
     const double cdt = cg * dt, ch2 = cg * h2, ch6 = cg * h6;  // k is solved without the factor -ue/dz (scan_row)
+    const int det = (int)detector_of(cp.detector_cell, nz);     // where outlet and summary are sampled
+    const int t_out = det / M, j_out = det - t_out * M;
+    const bool out_thread = (tid == t_out);
     __syncthreads();  // the previous column's readers of shared memory are done
     if (tid < N) {
       const chrom_species sp = b.species[cp.species_off + tid];
@@ -207,16 +208,16 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
 #pragma unroll
       for (int s = 0; s < N; ++s) {
         const double v0 = out_value(s);
-        if (b.outlet) b.outlet[((size_t)col * N + s) * b.n_out] = v0;
-        summ[s][0] = 0.0;
-        summ[s][1] = 0.0;
-        summ[s][2] = v0;
-        summ[s][3] = 0.0;
-        summ[s][4] = v0;
+        if (b.outlet && sample_has_initial(b.out_steps, b.outlet_stride)) b.outlet[((size_t)col * N + s) * b.n_out] = v0;
+        summ_init(summ[s], v0);
       }
     }
-    if (b.snapshots) store_profile(b.snapshots + (size_t)col * b.n_snap * N * nz);
-    uint32_t out_count = b.outlet_stride, snap_count = b.snapshot_stride, out_slot = 1, snap_slot = 1;
+    if (b.snapshots && sample_has_initial(b.snap_steps, b.snapshot_stride))
+      store_profile(b.snapshots + (size_t)col * b.n_snap * N * nz);
+    SampleCursor oc = sample_begin(b.out_steps, b.n_out, b.outlet ? b.outlet_stride : 0u, 0u);
+    SampleCursor sc_ = sample_begin(b.snap_steps, b.n_snap, b.snapshots ? b.snapshot_stride : 0u, 0u);
+    if (!b.outlet) oc.next = kNoSample;
+    if (!b.snapshots) sc_.next = kNoSample;
     bool done = false;
 
     // One stage over this thread's cells: k = f(src), then the stage algebra `which`
@@ -326,43 +327,25 @@ __global__ void __launch_bounds__(reg_max_threads(N, M), 1) k_multi_reg(const Ba
       maybe = hi_nonfinite(mx);
 
       // ---- samples --------------------------------------------------------------------------------
-      const bool out_now = (b.outlet != nullptr) && (--out_count == 0);
-      if (out_now) out_count = b.outlet_stride;
+      const bool out_now = (step + 1u == oc.next);
       if (out_thread && (out_now || b.summary != nullptr)) {
 #pragma unroll
         for (int s = 0; s < N; ++s) {
           const double v = out_value(s);
-          if (out_now) b.outlet[((size_t)col * N + s) * b.n_out + out_slot] = v;
-          if (b.summary) {
-            const double t0 = (double)step * dt, t1 = ((double)step + 1.0) * dt;
-            const double w = 0.5 * (t1 - t0);
-            summ[s][0] = fma(w, summ[s][4] + v, summ[s][0]);
-            summ[s][1] = fma(w, fma(t0, summ[s][4], t1 * v), summ[s][1]);
-            if (v > summ[s][2]) {
-              summ[s][2] = v;
-              summ[s][3] = t1;
-            }
-            summ[s][4] = v;
-          }
+          if (out_now) b.outlet[((size_t)col * N + s) * b.n_out + oc.k] = v;
+          if (b.summary) summ_step(summ[s], v, step, dt);
         }
       }
-      if (out_now) ++out_slot;
-      if (b.snapshots != nullptr && --snap_count == 0) {
-        snap_count = b.snapshot_stride;
-        store_profile(b.snapshots + ((size_t)col * b.n_snap + snap_slot) * N * nz);
-        ++snap_slot;
+      if (out_now) sample_advance(oc, b.out_steps, b.outlet_stride);
+      if (step + 1u == sc_.next) {
+        store_profile(b.snapshots + ((size_t)col * b.n_snap + sc_.k) * N * nz);
+        sample_advance(sc_, b.snap_steps, b.snapshot_stride);
       }
     }
     if (b.final_state) store_profile(b.final_state + (size_t)col * N * nz);
     if (out_thread && b.summary) {
 #pragma unroll
-      for (int s = 0; s < N; ++s) {
-        double* o = b.summary + ((size_t)col * N + s) * 4;
-        o[0] = summ[s][0];
-        o[1] = (summ[s][0] != 0.0) ? summ[s][1] / summ[s][0] : 0.0;
-        o[2] = summ[s][2];
-        o[3] = summ[s][3];
-      }
+      for (int s = 0; s < N; ++s) summ_store(b.summary + ((size_t)col * N + s) * CHROM_SUMMARY_LEN, summ[s]);
     }
   }
 }

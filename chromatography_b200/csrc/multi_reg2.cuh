@@ -6,16 +6,27 @@
 // AROUND the arithmetic, because ncu showed k_multi_reg bound by the shared-memory pipe and the CTA barrier, not by
 // FP64 (profiles/r1_ncu_full_multi_reg_c5.txt: FP64 pipe 40 %, l1tex 67 %, ~80 shared-memory wavefronts per warp and
 // cell-stage against 270 FP64-pipe cycles spread over 4 sub-partitions):
-//   * the running slope acc stays in registers (no private shared-memory slots);
-//   * the species constants {K, feNK, a0} are either held in registers (KREG, when a thread owns few enough
-//     doubles) or read as ONE 128-bit + one 64-bit broadcast load per species and cell;
+//   * a thread owns M = 2 contiguous cells with y, the stage state u AND the running slope acc in registers
+//     (no private shared-memory slots): 256 threads for a 512-cell column, 8 warps per SM at <= 255 registers;
+//   * the species constants {K, feNK, a0} are read once per column with uniform addresses: ptxas keeps them in
+//     UNIFORM registers (DFMA R, R, UR, R), so they cost neither shared-memory loads nor vector registers;
 //   * the upstream neighbour of a thread's first cell comes by warp shuffle; only the value that crosses a WARP
 //     boundary goes through shared memory, into a ring of 8 stage slots guarded by a per-warp release/acquire
-//     counter — a warp waits for its upstream warp only, never for the whole CTA;
+//     counter - a warp waits for its upstream warp only, never for the whole CTA.  Cells run in descending order,
+//     so the value the downstream warp needs (the LAST cell) is ready first and is posted at once, and the value a
+//     warp needs from upstream (for its FIRST cell) is awaited last: a full stage of slack between the two;
 //   * ONE __syncthreads per time step (it bounds how far a warp may run ahead, which makes the 8-slot ring safe, and
 //     publishes the step's inlet row) instead of one per stage plus a vote;
+//   * the hot path is straight-line code: the sufficient no-row-exchange bound only raises a flag, the per-step
+//     pivoting test and the dense fallback sit behind one warp vote per cell, and the fallback takes its operands
+//     through a shared-memory scratch block (a by-value vector across a call makes ptxas keep the hot result array in
+//     local memory as well: 16 local-memory accesses per stage in the first version of this kernel);
 //   * validate_state: every thread remembers the first step at which one of its own cells turned non-finite
 //     (a non-finite cell never becomes finite again); the column's status is the minimum of those keys.
+// Measured on B200 (C5, 4096 columns x nz 512 x n 8 x 4096 RK4 steps): 645 ms -> 471 ms.  Alternatives measured and
+// dropped (same workload): a rolled loop over the four stages 586 ms, one cell per thread with 16 warps 550 ms, the
+// two cells solved side by side 564 ms, no per-step barrier (warps skewed behind a consumed-counter) 599 ms, the n
+// reciprocals started from D instead of 1/D 501 ms, the constants through shared memory 603 ms.
 #pragma once
 #include "multi_reg.cuh"
 
@@ -31,13 +42,11 @@ __device__ __forceinline__ void st_release_cta(unsigned* p, unsigned v) {
   asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 
-// doubles a thread keeps live: y, u, acc (3 M N), constants (3 N when KREG), z and v of the cell being solved (2 N),
-// the upstream cell (N)  ->  registers ~ 2x + overhead; thread limit in steps of 128 (see reg_max_threads).
-// (KREG: the constants are read once per column with uniform addresses and ptxas keeps them in UNIFORM registers,
-// so they do not count against the vector register file.)
-constexpr int reg2_budget(int N, int M, bool /*KREG*/) { return 2 * (3 * M * N + 3 * N) + 30; }
-constexpr int reg2_max_threads(int N, int M, bool KREG) {
-  const int w = 512 / reg2_budget(N, M, KREG);
+// doubles a thread keeps live: y, u, acc (3 M N), z and v of the cell being solved (2 N), the upstream cell (N)
+// ->  registers ~ 2x + overhead; thread limit in steps of 128 (see reg_max_threads).
+constexpr int reg2_budget(int N, int M) { return 2 * (3 * M * N + 3 * N) + 30; }
+constexpr int reg2_max_threads(int N, int M) {
+  const int w = 512 / reg2_budget(N, M);
   return w < 1 ? 128 : (w > 8 ? 1024 : 128 * w);
 }
 
@@ -113,51 +122,42 @@ __device__ __noinline__ void dense_fallback_smem(const SpeciesConst* sc, double*
 
 // One cell: x solves (diag(alpha) - p q^T) x = c - up (the factor -ue/dz lives in the stage coefficients).
 // Returns true when the sufficient no-row-exchange bound fails (the caller then runs pivot_test on the cell).
-// Straight-line code: several cells of a thread can be solved side by side with their chains interleaved.
-template <int N, bool KREG>
-__device__ __forceinline__ bool solve_cell(const SpeciesConst* sc, const Consts<KREG ? N : 1>& kc, double kmax2,
-                                           double a0min, const double (&c)[N], const double (&up)[N], double (&x)[N]) {
-  double v[N];
-  double S0 = 0.0, S1 = 0.0;
+// The three dot products (S = q.c, q.v, q.z) are accumulated in kSums interleaved partial sums.  Two measured best on
+// C5 (465 ms; four partial sums 478 ms: the shorter chains do not pay for the additions that join them).
+#ifndef CHROM_REG2_SUMS
+#define CHROM_REG2_SUMS 2
+#endif
+template <int N>
+__device__ __forceinline__ bool solve_cell(const Consts<N>& kc, double kmax2, double a0min, const double (&c)[N],
+                                           const double (&up)[N], double (&x)[N]) {
+  constexpr int kSums = (CHROM_REG2_SUMS < N) ? CHROM_REG2_SUMS : (N > 1 ? N : 1);
+  auto join = [](const double (&p)[kSums]) {
+    double t = p[0];
 #pragma unroll
-  for (int s = 0; s < N; ++s) {
-    const double Ks = KREG ? kc.K[s] : sc[s].K;
-    if (s & 1) S1 = fma(Ks, c[s], S1);
-    else S0 = fma(Ks, c[s], S0);
-  }
-  const double rD = fast_rcp(1.0 + (S0 + S1));
+    for (int k = 1; k < kSums; ++k) t += p[k];
+    return t;
+  };
+  double v[N];
+  double S[kSums] = {};
+#pragma unroll
+  for (int s = 0; s < N; ++s) S[s % kSums] = fma(kc.K[s], c[s], S[s % kSums]);
+  const double rD = fast_rcp(1.0 + join(S));
   const double rD2 = rD * rD;
   unsigned pmax_hi = 0u;  // max over the high words of feNK_s c_s (monotone for non-negative doubles; a negative or
                           // non-finite entry reads as huge): one integer max per species
-  double qv0 = 0.0, qv1 = 0.0, qz0 = 0.0, qz1 = 0.0;
+  double qv[kSums] = {}, qz[kSums] = {};
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    double Ki, fi, ai;
-    if (KREG) {
-      Ki = kc.K[i];
-      fi = kc.feNK[i];
-      ai = kc.a0[i];
-    } else {
-      const double2 af = *reinterpret_cast<const double2*>(&sc[i].a0);  // {a0, feNK}
-      ai = af.x;
-      fi = af.y;
-      Ki = sc[i].K;
-    }
-    const double tc = fi * c[i];                  // p_i D^2
-    const double ra = fast_rcp(fma(fi, rD, ai));  // 1 / alpha_i
+    const double tc = kc.feNK[i] * c[i];                        // p_i D^2
+    const double ra = fast_rcp(fma(kc.feNK[i], rD, kc.a0[i]));  // 1 / alpha_i
     pmax_hi = max(pmax_hi, (unsigned)__double2hiint(tc));
     x[i] = (c[i] - up[i]) * ra;  // z_i
     v[i] = tc * ra;              // v_i D^2
-    if (i & 1) {
-      qv1 = fma(Ki, v[i], qv1);
-      qz1 = fma(Ki, x[i], qz1);
-    } else {
-      qv0 = fma(Ki, v[i], qv0);
-      qz0 = fma(Ki, x[i], qz0);
-    }
+    qv[i % kSums] = fma(kc.K[i], v[i], qv[i % kSums]);
+    qz[i % kSums] = fma(kc.K[i], x[i], qz[i % kSums]);
   }
-  const double hn = fma(-rD2, qv0 + qv1, 1.0);  // 1 - q.v
-  const double g = ((qz0 + qz1) * fast_rcp(hn)) * rD2;
+  const double hn = fma(-rD2, join(qv), 1.0);  // 1 - q.v
+  const double g = (join(qz) * rD2) * fast_rcp(hn);
 #pragma unroll
   for (int i = 0; i < N; ++i) x[i] = fma(v[i], g, x[i]);
   // Sufficient for "no row exchange anywhere": 2 max q max|p| < min alpha (1 - q.v), with alpha_i >= a0_i when every
@@ -201,20 +201,16 @@ __device__ __forceinline__ bool pivot_test(const SpeciesConst* sc, const double 
   return redo;
 }
 
-// ROLL : the four RK4 stages as a rolled loop.  FREE : no per-step barrier - warps run skewed behind their upstream
-// warp, the ring is protected by a consumed-counter per warp.  INTER : the cells of a thread are solved side by side
-// (their dependency chains interleave) instead of one after the other.
-template <int N, int M, int METHOD, bool KREG, bool ROLL, bool FREE, bool INTER>
-__global__ void __launch_bounds__(reg2_max_threads(N, M, KREG), 1) k_multi_reg2(const BatchDev b) {
+template <int N, int M, int METHOD>
+__global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg2(const BatchDev b) {
   constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
   constexpr int XS = N | 1;  // seam rows: odd stride
   __shared__ SpeciesConst sc[N];
   __shared__ double inlet[2][3][N];  // [step parity][stage row][species]
-  __shared__ double summ[N][5];      // area, moment, max, tmax, previous sample (outlet owner only)
+  __shared__ Summ summ[N];           // running summary of the detector signal (detector owner only)
   __shared__ const double* tabs[N];
   __shared__ double colc[2];              // 2 max_i K_i, min_i (1 + fe lambda_i) of the current column
   __shared__ unsigned flags[32];          // per warp: stage inputs posted so far in this column
-  __shared__ unsigned consumed[32];       // per warp: stage inputs read from the upstream warp's ring so far (FREE)
   __shared__ unsigned long long badkey;   // min over threads of (first bad step << 1) | (NaN ? 0 : 1); ~0 = clean
   extern __shared__ double seam[];        // [8 slots][W warps][XS]: the last cell of each warp, per stage input;
                                           // then cold[W][3 N + N N]: the dense-fallback scratch block of each warp
@@ -225,8 +221,6 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M, KREG), 1) k_multi_reg2(
   const uint32_t nz = b.nz;
   const int cell0 = tid * M;
   const int nv = max(0, min(M, (int)nz - cell0));  // real cells of this thread
-  const int t_out = (int)(nz - 1) / M, j_out = (int)(nz - 1) - t_out * M;
-  const bool out_thread = (tid == t_out);
   const double dt = b.dt, h2 = b.half_dt, h6 = b.sixth_dt;
   const uint32_t steps = b.steps;
 
@@ -236,6 +230,9 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M, KREG), 1) k_multi_reg2(
     const double cg = -cp.ue / cp.dz;
     const double cdt = cg * dt, ch2 = cg * h2, ch6 = cg * h6;  // x is solved without the factor -ue/dz
     const double cfin = (METHOD == CHROM_RK4) ? ch6 : cdt;      // coefficient of the closing update
+    const int det = (int)detector_of(cp.detector_cell, nz);     // where outlet and summary are sampled
+    const int t_out = det / M, j_out = det - t_out * M;
+    const bool out_thread = (tid == t_out);
     __syncthreads();  // the previous column's readers of shared memory are done
     if (tid < N) {
       const chrom_species sp = b.species[cp.species_off + tid];
@@ -253,10 +250,7 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M, KREG), 1) k_multi_reg2(
       sc[tid] = q;
       tabs[tid] = b.tables + (size_t)sp.inj_table * steps * ST;
     }
-    if (tid < 32) {
-      flags[tid] = 0u;
-      consumed[tid] = 0u;
-    }
+    if (tid < 32) flags[tid] = 0u;
     if (tid == 0) badkey = ~0ull;
     double y[M][N], u[M][N], acc[M][N];
 #pragma unroll
@@ -267,7 +261,7 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M, KREG), 1) k_multi_reg2(
         u[j][s] = y[j][s];
         acc[j][s] = 0.0;
       }
-    auto out_value = [&](int s) -> double {  // species s of the outlet cell (meaningful on out_thread)
+    auto out_value = [&](int s) -> double {  // species s of the detector cell (meaningful on out_thread)
       double v = y[M - 1][s];
 #pragma unroll
       for (int j = 0; j < M - 1; ++j) v = (j == j_out) ? y[j][s] : v;
@@ -281,14 +275,12 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M, KREG), 1) k_multi_reg2(
           for (int s = 0; s < N; ++s) dst[(size_t)s * nz + cell0 + j] = y[j][s];
     };
     __syncthreads();
-    Consts<KREG ? N : 1> kc;
-    if (KREG) {
+    Consts<N> kc;  // uniform addresses: these land in uniform registers
 #pragma unroll
-      for (int s = 0; s < (KREG ? N : 1); ++s) {
-        kc.K[s] = sc[s].K;
-        kc.feNK[s] = sc[s].feNK;
-        kc.a0[s] = sc[s].a0;
-      }
+    for (int s = 0; s < N; ++s) {
+      kc.K[s] = sc[s].K;
+      kc.feNK[s] = sc[s].feNK;
+      kc.a0[s] = sc[s].a0;
     }
     if (tid == 0) {
       double km = 0.0, am = 1e300;
@@ -304,98 +296,65 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M, KREG), 1) k_multi_reg2(
 #pragma unroll
       for (int s = 0; s < N; ++s) {
         const double v0 = out_value(s);
-        if (b.outlet) b.outlet[((size_t)col * N + s) * b.n_out] = v0;
-        summ[s][0] = 0.0;
-        summ[s][1] = 0.0;
-        summ[s][2] = v0;
-        summ[s][3] = 0.0;
-        summ[s][4] = v0;
+        if (b.outlet && sample_has_initial(b.out_steps, b.outlet_stride)) b.outlet[((size_t)col * N + s) * b.n_out] = v0;
+        summ_init(summ[s], v0);
       }
     }
-    if (b.snapshots) store_profile(b.snapshots + (size_t)col * b.n_snap * N * nz);
-    uint32_t out_count = b.outlet_stride, snap_count = b.snapshot_stride, out_slot = 1, snap_slot = 1;
+    if (b.snapshots && sample_has_initial(b.snap_steps, b.snapshot_stride))
+      store_profile(b.snapshots + (size_t)col * b.n_snap * N * nz);
+    SampleCursor oc = sample_begin(b.out_steps, b.n_out, b.outlet ? b.outlet_stride : 0u, 0u);
+    SampleCursor sc_ = sample_begin(b.snap_steps, b.n_snap, b.snapshots ? b.snapshot_stride : 0u, 0u);
+    if (!b.outlet) oc.next = kNoSample;
+    if (!b.snapshots) sc_.next = kNoSample;
     unsigned posted = 0u;  // stage inputs this warp has posted (uniform over the CTA: every warp posts every one)
-    if (FREE) __syncthreads();  // colc, flags and the summary slots are set; no barrier inside the time loop
     bool recorded = false;
 
-    // The last cell of a stage's OUTPUT (= the next stage's input) goes to a ring slot for the downstream warp:
-    // lane 31 stores, then publishes with a release store of the new count.  With the per-step barrier the slot is
-    // (step parity, stage) and the barrier keeps the ring safe; FREE: slot = count mod 8, and the producer first
-    // waits until the downstream warp has consumed the entry that slot held (8 posts ago).
+    // The last cell of a stage's OUTPUT (= the next stage's input) goes to ring slot `slot` (step parity, stage) for
+    // the downstream warp: lane 31 stores, then publishes with a release store of the new count.  The per-step
+    // barrier keeps the ring safe: a slot is written again two steps later.
     auto post = [&](const double (&last)[N], int slot) {
       ++posted;
       if (lane == 31 && warp + 1 < W) {
-        if (FREE) {
-          slot = (int)((posted - 1u) & 7u);
-          if (posted > 8u) {
-            const unsigned need = posted - 8u;
-            while ((int)(ld_acquire_cta(&consumed[warp + 1]) - need) < 0) {
-            }
-          }
-        }
         double* dst = seam + ((size_t)slot * W + warp) * XS;
 #pragma unroll
         for (int s = 0; s < N; ++s) dst[s] = last[s];
         st_release_cta(&flags[warp], posted);
       }
     };
-    // The upstream cell of this warp's first lane for the stage input number `need` (1-based count).
-    auto fetch_up = [&](double (&up)[N], int irow, int spar, int slot, unsigned need) {
-      if (lane == 0) {  // the inlet (warp 0) or the upstream warp's last cell
-        if (warp == 0) {
-#pragma unroll
-          for (int s = 0; s < N; ++s) up[s] = inlet[spar][irow][s];
-        } else {
-          while ((int)(ld_acquire_cta(&flags[warp - 1]) - need) < 0) {
-          }
-          if (FREE) slot = (int)((need - 1u) & 7u);
-          const double* srcp = seam + ((size_t)slot * W + (warp - 1)) * XS;
-#pragma unroll
-          for (int s = 0; s < N; ++s) up[s] = srcp[s];
-          if (FREE) st_release_cta(&consumed[warp], need);
-        }
-      }
-    };
 
     // One stage over this thread's cells.  Invariant at the top of a step: u == y, acc == 0.  Every stage solves
     // k = f(u), accumulates acc += w k (w = 1, 2, 2, 1: rk4.rs:311) and forms the next stage state u = y + cu k
-    // (cu = dt/2, dt/2, dt); the last one forms y += acc dt/6 (Euler: y += k dt) and restores the invariant.  The
-    // arithmetic is that of the four hand-written stages (acc = k1 is 0 + 1 k1, exactly), so a rolled stage loop
-    // (ROLL: a quarter of the code) gives the same bits.
-    // Cells run in DESCENDING order (cell j reads u[j - 1] before that cell is overwritten in place), so the value
-    // the downstream warp needs - this thread's LAST cell - is ready first and is posted at once, and the value this
-    // warp needs from upstream - for its FIRST cell - is awaited last: a full stage of slack between the two.
-    // INTER: all cells are solved before any is updated (independent chains side by side), one vote for the rare
-    // paths; the upstream value is then needed at the start and the post comes at the end.
+    // (cu = dt/2, dt/2, dt); the last one forms y += acc dt/6 (Euler: y += k dt) and restores the invariant.
+    // (acc = k1 is 0 + 1 k1 exactly, so this is the arithmetic of rk4.rs:284-311 term by term.)
     auto stage = [&](int irow, int spar, int slot, int slot_next, double wk, double cuk, bool last) {
       double up[N];
 #pragma unroll
       for (int s = 0; s < N; ++s) up[s] = __shfl_up_sync(0xffffffffu, u[M - 1][s], 1);
       const double kmax2 = colc[0], a0min = colc[1];
-      const unsigned need_in = posted;  // inputs this warp had posted when the stage began
-      auto rare = [&](int j, const double (&upv)[N], double (&x)[N], bool suspect) {
-        // rare paths of one cell: the per-step pivoting test, then the dense row-exchanging LU, one flagged cell at
-        // a time on the warp's scratch block
-        bool redo = false;
-        if (suspect) redo = pivot_test<N>(sc, u[j]);
-        const unsigned need_lu = __ballot_sync(0xffffffffu, redo);
-        double* w = cold + (size_t)warp * (2 * N + N * N + N);
-        for (unsigned m = need_lu; m != 0u; m &= m - 1u) {
-          const int src_lane = __ffs((int)m) - 1;
-          if (lane == src_lane) {
+      auto cell = [&](int j, const double (&upv)[N]) {
+        double x[N];
+        const bool suspect = solve_cell<N>(kc, kmax2, a0min, u[j], upv, x);
+        if (__any_sync(0xffffffffu, suspect)) {
+          // rare: the per-step pivoting test, then the dense row-exchanging LU, one flagged cell at a time on the
+          // warp's scratch block
+          bool redo = false;
+          if (suspect) redo = pivot_test<N>(sc, u[j]);
+          double* w = cold + (size_t)warp * (2 * N + N * N + N);
+          for (unsigned m = __ballot_sync(0xffffffffu, redo); m != 0u; m &= m - 1u) {
+            const int src_lane = __ffs((int)m) - 1;
+            if (lane == src_lane) {
 #pragma unroll
-            for (int s = 0; s < N; ++s) {
-              w[s] = u[j][s];
-              w[N + s] = upv[s];
+              for (int s = 0; s < N; ++s) {
+                w[s] = u[j][s];
+                w[N + s] = upv[s];
+              }
+              dense_fallback_smem(sc, w, N);
+#pragma unroll
+              for (int s = 0; s < N; ++s) x[s] = w[s];
             }
-            dense_fallback_smem(sc, w, N);
-#pragma unroll
-            for (int s = 0; s < N; ++s) x[s] = w[s];
+            __syncwarp();
           }
-          __syncwarp();
         }
-      };
-      auto update = [&](int j, const double (&x)[N]) {
 #pragma unroll
         for (int s = 0; s < N; ++s) {
           acc[j][s] = fma(x[s], wk, acc[j][s]);
@@ -408,79 +367,46 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M, KREG), 1) k_multi_reg2(
           }
         }
       };
-      if (INTER) {
-        fetch_up(up, irow, spar, slot, need_in);
-        double x[M][N];
-        bool suspect[M];
-        bool any = false;
+      // cells in DESCENDING order: cell j reads u[j - 1] before that cell is overwritten in place; the last cell is
+      // posted as soon as it is done
 #pragma unroll
-        for (int j = M - 1; j >= 0; --j) {
-          suspect[j] = (j > 0) ? solve_cell<N, KREG>(sc, kc, kmax2, a0min, u[j], u[j - 1], x[j])
-                               : solve_cell<N, KREG>(sc, kc, kmax2, a0min, u[0], up, x[0]);
-          any |= suspect[j];
-        }
-        if (__any_sync(0xffffffffu, any)) {
-#pragma unroll
-          for (int j = M - 1; j >= 0; --j) {
-            if (j > 0) rare(j, u[j - 1], x[j], suspect[j]);
-            else rare(0, up, x[0], suspect[0]);
-          }
-        }
-#pragma unroll
-        for (int j = M - 1; j >= 0; --j) update(j, x[j]);
-        post(u[M - 1], slot_next);
-      } else {
-        auto cell = [&](int j, const double (&upv)[N]) {
-          double x[N];
-          const bool suspect = solve_cell<N, KREG>(sc, kc, kmax2, a0min, u[j], upv, x);
-          if (__any_sync(0xffffffffu, suspect)) rare(j, upv, x, suspect);
-          update(j, x);
-        };
-#pragma unroll
-        for (int j = M - 1; j >= 1; --j) {
-          cell(j, u[j - 1]);
-          if (j == M - 1) post(u[M - 1], slot_next);
-        }
-        fetch_up(up, irow, spar, slot, posted - (M > 1 ? 1u : 0u));
-        cell(0, up);
-        if (M == 1) post(u[0], slot_next);
+      for (int j = M - 1; j >= 1; --j) {
+        cell(j, u[j - 1]);
+        if (j == M - 1) post(u[M - 1], slot_next);
       }
+      if (lane == 0) {  // the first lane's upstream cell: the inlet (warp 0) or the upstream warp's last cell
+        if (warp == 0) {
+#pragma unroll
+          for (int s = 0; s < N; ++s) up[s] = inlet[spar][irow][s];
+        } else {
+          const unsigned need = posted - (M > 1 ? 1u : 0u);  // inputs this warp had posted when the stage began
+          while ((int)(ld_acquire_cta(&flags[warp - 1]) - need) < 0) {
+          }
+          const double* srcp = seam + ((size_t)slot * W + (warp - 1)) * XS;
+#pragma unroll
+          for (int s = 0; s < N; ++s) up[s] = srcp[s];
+        }
+      }
+      cell(0, up);
+      if (M == 1) post(u[0], slot_next);
     };
 
     post(y[M - 1], 0);  // input of stage 1 of step 0
     for (uint32_t step = 0; step < steps; ++step) {
       const int spar = (int)(step & 1u);
-      if (FREE) {
-        // only the first lane of warp 0 reads the inlet: warp 0 loads the step's row itself, no CTA-wide barrier
-        if (warp == 0) {
-          for (int i = lane; i < N * ST; i += 32) {
-            const int s = i % N, r = i / N;
-            inlet[spar][r][s] = tabs[s][(size_t)step * ST + r];
-          }
-          __syncwarp();
-        }
-      } else {
-        for (int i = tid; i < N * ST; i += (int)blockDim.x) {  // inlet values of this step: [stage row][species]
-          const int s = i % N, r = i / N;
-          inlet[spar][r][s] = tabs[s][(size_t)step * ST + r];
-        }
-        // The ONE barrier of the step: publishes the inlet row and keeps every warp within one step of the others
-        // (ring slots are reused two steps later).
-        __syncthreads();
+      for (int i = tid; i < N * ST; i += (int)blockDim.x) {  // inlet values of this step: [stage row][species]
+        const int s = i % N, r = i / N;
+        inlet[spar][r][s] = tabs[s][(size_t)step * ST + r];
       }
+      // The ONE barrier of the step: publishes the inlet row and keeps every warp within one step of the others
+      // (ring slots are reused two steps later).
+      __syncthreads();
       const int s0 = spar * 4, s1 = (spar ^ 1) * 4;
       if (METHOD == CHROM_RK4) {
-        if (ROLL) {
-#pragma unroll 1
-          for (int k = 0; k < 4; ++k)
-            stage((k + 1) >> 1, spar, s0 + k, k < 3 ? s0 + k + 1 : s1, (k == 1 || k == 2) ? 2.0 : 1.0,
-                  k == 2 ? cdt : ch2, k == 3);
-        } else {
-          stage(0, spar, s0 + 0, s0 + 1, 1.0, ch2, false);
-          stage(1, spar, s0 + 1, s0 + 2, 2.0, ch2, false);
-          stage(1, spar, s0 + 2, s0 + 3, 2.0, cdt, false);
-          stage(2, spar, s0 + 3, s1 + 0, 1.0, ch2, true);
-        }
+        stage(0, spar, s0 + 0, s0 + 1, 1.0, ch2, false);
+        stage(1, spar, s0 + 1, s0 + 2, 2.0, ch2, false);
+        stage(1, spar, s0 + 2, s0 + 3, 2.0, cdt, false);
+        stage(2, spar, s0 + 3, s1 + 0, 1.0, ch2, true);
       } else {
         stage(0, spar, s0 + 0, s1 + 0, 1.0, cdt, true);
       }
@@ -507,43 +433,25 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M, KREG), 1) k_multi_reg2(
       }
 
       // ---- samples --------------------------------------------------------------------------------
-      const bool out_now = (b.outlet != nullptr) && (--out_count == 0);
-      if (out_now) out_count = b.outlet_stride;
+      const bool out_now = (step + 1u == oc.next);
       if (out_thread && (out_now || b.summary != nullptr)) {
 #pragma unroll
         for (int s = 0; s < N; ++s) {
           const double v = out_value(s);
-          if (out_now) b.outlet[((size_t)col * N + s) * b.n_out + out_slot] = v;
-          if (b.summary) {
-            const double t0 = (double)step * dt, t1 = ((double)step + 1.0) * dt;
-            const double w = 0.5 * (t1 - t0);
-            summ[s][0] = fma(w, summ[s][4] + v, summ[s][0]);
-            summ[s][1] = fma(w, fma(t0, summ[s][4], t1 * v), summ[s][1]);
-            if (v > summ[s][2]) {
-              summ[s][2] = v;
-              summ[s][3] = t1;
-            }
-            summ[s][4] = v;
-          }
+          if (out_now) b.outlet[((size_t)col * N + s) * b.n_out + oc.k] = v;
+          if (b.summary) summ_step(summ[s], v, step, dt);
         }
       }
-      if (out_now) ++out_slot;
-      if (b.snapshots != nullptr && --snap_count == 0) {
-        snap_count = b.snapshot_stride;
-        store_profile(b.snapshots + ((size_t)col * b.n_snap + snap_slot) * N * nz);
-        ++snap_slot;
+      if (out_now) sample_advance(oc, b.out_steps, b.outlet_stride);
+      if (step + 1u == sc_.next) {
+        store_profile(b.snapshots + ((size_t)col * b.n_snap + sc_.k) * N * nz);
+        sample_advance(sc_, b.snap_steps, b.snapshot_stride);
       }
     }
     if (b.final_state) store_profile(b.final_state + (size_t)col * N * nz);
     if (out_thread && b.summary) {
 #pragma unroll
-      for (int s = 0; s < N; ++s) {
-        double* o = b.summary + ((size_t)col * N + s) * 4;
-        o[0] = summ[s][0];
-        o[1] = (summ[s][0] != 0.0) ? summ[s][1] / summ[s][0] : 0.0;
-        o[2] = summ[s][2];
-        o[3] = summ[s][3];
-      }
+      for (int s = 0; s < N; ++s) summ_store(b.summary + ((size_t)col * N + s) * CHROM_SUMMARY_LEN, summ[s]);
     }
     __syncthreads();  // every thread's atomicMin on badkey has landed
     if (tid == 0 && b.status && badkey != ~0ull) {
@@ -553,34 +461,15 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M, KREG), 1) k_multi_reg2(
   }
 }
 
-// variants (species constants in uniform registers throughout):
-//   2 = 2 cells per thread, four hand-written stages, per-step barrier        4 = the same, rolled stage loop
-//   5 = 1 cell per thread, rolled, per-step barrier                           7 = 1 cell, rolled, FREE (no barrier)
-//   6 = 2 cells solved side by side, rolled, FREE                             8 = 2 cells one after the other, rolled, FREE
 template <int N>
-rkern_t pick_reg2_n(int method, int variant) {
-  if constexpr (N >= 1 && N <= 8) {
-    const bool rk4 = method == CHROM_RK4;
-    switch (variant) {
-      case 2: return rk4 ? k_multi_reg2<N, 2, CHROM_RK4, true, false, false, false> : k_multi_reg2<N, 2, CHROM_EULER, true, false, false, false>;
-      case 4: return rk4 ? k_multi_reg2<N, 2, CHROM_RK4, true, true, false, false> : k_multi_reg2<N, 2, CHROM_EULER, true, false, false, false>;
-      case 5: return rk4 ? k_multi_reg2<N, 1, CHROM_RK4, true, true, false, false> : k_multi_reg2<N, 1, CHROM_EULER, true, false, false, false>;
-      case 6: return rk4 ? k_multi_reg2<N, 2, CHROM_RK4, true, true, true, true> : k_multi_reg2<N, 2, CHROM_EULER, true, false, true, true>;
-      case 7: return rk4 ? k_multi_reg2<N, 1, CHROM_RK4, true, true, true, false> : k_multi_reg2<N, 1, CHROM_EULER, true, false, true, false>;
-      case 8: return rk4 ? k_multi_reg2<N, 2, CHROM_RK4, true, true, true, false> : k_multi_reg2<N, 2, CHROM_EULER, true, false, true, false>;
-    }
-  }
+rkern_t pick_reg2_n(int method) {
+  if constexpr (N >= 1 && N <= 8) return method == CHROM_RK4 ? k_multi_reg2<N, 2, CHROM_RK4> : k_multi_reg2<N, 2, CHROM_EULER>;
   return nullptr;
 }
 
 template <int N>
-int reg2_tmax_rt(int variant) {
-  if constexpr (N >= 1 && N <= 8) {
-    switch (variant) {
-      case 5: case 7: return reg2_max_threads(N, 1, true);
-      case 2: case 4: case 6: case 8: return reg2_max_threads(N, 2, true);
-    }
-  }
+int reg2_tmax_rt() {
+  if constexpr (N >= 1 && N <= 8) return reg2_max_threads(N, 2);
   return 0;
 }
 

@@ -59,7 +59,7 @@ mkern_t lookup_multi(int n, int method, int arith) {
 }
 
 size_t multi_smem_bytes(int n, uint32_t nz) {
-  return ((size_t)4 * n * nz + 3 * n + 5 * n) * sizeof(double) + (size_t)n * kSpeciesConstBytes;
+  return ((size_t)4 * n * nz + 3 * n + kSummSlots * n) * sizeof(double) + (size_t)n * kSpeciesConstBytes;
 }
 
 }  // namespace

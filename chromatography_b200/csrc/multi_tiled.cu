@@ -58,9 +58,9 @@ tkern_t lookup_tiled(int n, int method, int arith, int wj) {
   return nullptr;
 }
 
-// shared memory of one tile: 4 state arrays [n][pitch], inlet [3][n], summary [n][5], SpeciesConst [n], table pointers [n]
+// shared memory of one tile: 4 state arrays [n][pitch], inlet [3][n], summary [n][kSummSlots], SpeciesConst [n], table pointers [n]
 size_t tiled_smem_bytes(int n, uint32_t pitch) {
-  return ((size_t)4 * n * pitch + 8 * (size_t)n) * sizeof(double) + (size_t)n * 10 * sizeof(double) + (size_t)n * sizeof(void*);
+  return ((size_t)4 * n * pitch + (3 + kSummSlots) * (size_t)n) * sizeof(double) + (size_t)n * 10 * sizeof(double) + (size_t)n * sizeof(void*);
 }
 
 int env_int(const char* name, int dflt) {
@@ -70,7 +70,7 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
-size_t multi_tiled_extra_doubles(uint32_t n_species) { return 1 + 5 * (size_t)n_species; }
+size_t multi_tiled_extra_doubles(uint32_t n_species) { return 1 + (size_t)kSummSlots * n_species; }
 
 size_t multi_tiled_scratch_doubles(const BatchDev& b, const LaunchGeom& g) {
   const size_t n = b.n_species;

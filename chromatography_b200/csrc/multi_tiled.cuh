@@ -412,8 +412,8 @@ __global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi
   double* U0 = ACC + plane;
   double* U1 = U0 + plane;
   double* inlet = U1 + plane;                        // [3][n]
-  double* summ = inlet + 3 * n;                      // [n][5]
-  SpeciesConst* sc = (SpeciesConst*)(summ + 5 * n);  // [n]
+  double* summ = inlet + 3 * n;                               // [n] Summ (kSummSlots doubles each)
+  SpeciesConst* sc = (SpeciesConst*)(summ + kSummSlots * n);  // [n]
   const double** tabs = (const double**)(sc + n);    // [n]
   double* warp_scratch = nullptr;                    // warp-per-cell scratch: a contiguous block per warp
   if (WJ > 0 && scratch)
@@ -428,7 +428,9 @@ __global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi
     const uint32_t base = tile * V;                       // tile 0: [0, tw); tile t: [t*V, t*V + tw), first `halo` discarded
     const uint32_t ncell = min(a.tw, nz - base);
     const uint32_t first_valid = tile ? a.halo : 0u;
-    const bool owns_outlet = (base + ncell == nz);
+    const uint32_t det = detector_of(b.mcols[col].detector_cell, nz);  // the detector cell, owned by exactly one tile
+    const bool owns_outlet = (det >= base + first_valid) && (det < base + ncell);
+    const uint32_t jd = det - base;  // its tile-local index (meaningful when owns_outlet)
     const chrom_multi_col cp = b.mcols[col];
     const double fe = cp.fe, ue = cp.ue, dz = cp.dz;
     const double cg = -ue / dz;
@@ -459,20 +461,14 @@ __global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi
     __syncthreads();
     if (owns_outlet)
       for (int s = tid; s < n; s += T) {
-        double* sm = summ + s * 5;
-        if (a.step0 == 0) {
-          const double v0 = Y[(size_t)s * pitch + ncell - 1];
-          sm[0] = 0.0;
-          sm[1] = 0.0;
-          sm[2] = v0;
-          sm[3] = 0.0;
-          sm[4] = v0;
-        } else {
-          const double* g = a.gsumm + ((size_t)col * n + s) * 5;
-#pragma unroll
-          for (int q = 0; q < 5; ++q) sm[q] = g[q];
-        }
+        Summ& sm = reinterpret_cast<Summ*>(summ)[s];
+        if (a.step0 == 0) summ_init(sm, Y[(size_t)s * pitch + jd]);
+        else sm = reinterpret_cast<const Summ*>(a.gsumm)[(size_t)col * n + s];
       }
+    SampleCursor oc = sample_begin(b.out_steps, b.n_out, b.outlet ? b.outlet_stride : 0u, a.step0);
+    SampleCursor sc_ = sample_begin(b.snap_steps, b.n_snap, b.snapshots ? b.snapshot_stride : 0u, a.step0);
+    if (!b.outlet) oc.next = kNoSample;
+    if (!b.snapshots) sc_.next = kNoSample;
     // warp per cell: the lane's species constants stay in registers for the whole tile
     double wK[WJC], wF[WJC], wA[WJC];
     double w_kmax = 0.0, w_a0min = 0.0;  // max_i K_i and min_i (1 + fe lambda_i) of the column (pivot bound)
@@ -622,30 +618,20 @@ __global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi
 
       // ---- samples (cells this tile owns) ----------------------------------------------------------
       const uint32_t done = step + 1u;
-      if (owns_outlet) {
-        const bool out_now = b.outlet && b.outlet_stride && (done % b.outlet_stride == 0u);
-        const uint32_t out_slot = out_now ? done / b.outlet_stride : 0u;
+      const bool out_now = (done == oc.next);
+      if (owns_outlet && (out_now || b.summary)) {
         for (int s = tid; s < n; s += T) {
-          const double v = Y[(size_t)s * pitch + ncell - 1];
-          if (out_now) b.outlet[((size_t)col * n + s) * b.n_out + out_slot] = v;
-          if (b.summary) {
-            const double t0 = (double)step * dt, t1 = ((double)step + 1.0) * dt;
-            const double w = 0.5 * (t1 - t0);
-            double* sm = summ + s * 5;
-            sm[0] = fma(w, sm[4] + v, sm[0]);
-            sm[1] = fma(w, fma(t0, sm[4], t1 * v), sm[1]);
-            if (v > sm[2]) {
-              sm[2] = v;
-              sm[3] = t1;
-            }
-            sm[4] = v;
-          }
+          const double v = Y[(size_t)s * pitch + jd];
+          if (out_now) b.outlet[((size_t)col * n + s) * b.n_out + oc.k] = v;
+          if (b.summary) summ_step(reinterpret_cast<Summ*>(summ)[s], v, step, dt);
         }
       }
-      if (b.snapshots && b.snapshot_stride && (done % b.snapshot_stride == 0u)) {
-        double* gdst = b.snapshots + ((size_t)col * b.n_snap + done / b.snapshot_stride) * n * nz + base;
+      if (out_now) sample_advance(oc, b.out_steps, b.outlet_stride);
+      if (done == sc_.next) {
+        double* gdst = b.snapshots + ((size_t)col * b.n_snap + sc_.k) * n * nz + base;
         for_tile(n, first_valid, ncell, tid, T,
                  [&](uint32_t s, uint32_t j) { gdst[(size_t)s * nz + j] = Y[(size_t)s * pitch + j]; });
+        sample_advance(sc_, b.snap_steps, b.snapshot_stride);
       }
       if (any_bad && !flagged) {  // validate_state: the first bad step wins, NaN over Inf within it
         bool has_nan = false;
@@ -663,11 +649,8 @@ __global__ void __launch_bounds__(WJ > 0 ? tiled_warp_threads(WJ, ARITH) : multi
     for_tile(n, first_valid, ncell, tid, T,
              [&](uint32_t s, uint32_t j) { gdst[(size_t)s * nz + j] = Y[(size_t)s * pitch + j]; });
     if (owns_outlet && b.summary)
-      for (int s = tid; s < n; s += T) {
-        double* g = a.gsumm + ((size_t)col * n + s) * 5;
-#pragma unroll
-        for (int q = 0; q < 5; ++q) g[q] = summ[s * 5 + q];
-      }
+      for (int s = tid; s < n; s += T)
+        reinterpret_cast<Summ*>(a.gsumm)[(size_t)col * n + s] = reinterpret_cast<const Summ*>(summ)[s];
   }
 }
 
@@ -680,8 +663,10 @@ __global__ void k_tiled_init(const BatchDev b, double* __restrict__ ping, unsign
     const double v = b.y0 ? b.y0[i] : 0.0;
     ping[i] = v;
     const size_t col = i / plane, r = i - col * plane;
-    if (b.snapshots) b.snapshots[col * b.n_snap * plane + r] = v;
-    if (b.outlet && (r % b.nz) == b.nz - 1) b.outlet[(col * b.n_species + r / b.nz) * b.n_out] = v;
+    if (b.snapshots && sample_has_initial(b.snap_steps, b.snapshot_stride)) b.snapshots[col * b.n_snap * plane + r] = v;
+    if (b.outlet && sample_has_initial(b.out_steps, b.outlet_stride) &&
+        (r % b.nz) == detector_of(b.mcols[col].detector_cell, b.nz))
+      b.outlet[(col * b.n_species + r / b.nz) * b.n_out] = v;
   }
   for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < b.n_cols; c += stride) code[c] = ~0ull;
 }
@@ -696,12 +681,7 @@ __global__ void k_tiled_finalize(const BatchDev b, const unsigned long long* __r
     b.status[i] = (c == ~0ull) ? 0ll : ((c & 1ull) ? -s : s);
   }
   if (i < b.n_cols * b.n_species && b.summary) {
-    const double* sm = gsumm + (size_t)i * 5;
-    double* o = b.summary + (size_t)i * 4;
-    o[0] = sm[0];
-    o[1] = (sm[0] != 0.0) ? sm[1] / sm[0] : 0.0;
-    o[2] = sm[2];
-    o[3] = sm[3];
+    summ_store(b.summary + (size_t)i * CHROM_SUMMARY_LEN, reinterpret_cast<const Summ*>(gsumm)[i]);
   }
 }
 

@@ -30,14 +30,16 @@ namespace {
 
 const char* arith_name(int a) { return a == CHROM_ARITH_EXACT ? "exact" : (a == CHROM_KARITH_POLY ? "fast-poly" : "fast"); }
 
-constexpr int kBlockThreads = 64;  // single-warp-per-column variant: 2 independent warps per CTA
+constexpr int kBlockThreads = 64;     // single-warp-per-column variant: 2 independent warps per CTA ...
+constexpr int kMaxBlockThreads = 128;  // ... or 4 (split launches: one warp per SM sub-partition and CTA)
 
+// resident 64-thread CTAs per SM the register file allows (255 / 168 / 128 registers per thread)
 constexpr int min_blocks_for(int M) { return M >= 17 ? 4 : (M >= 11 ? 6 : 8); }
 // multi-warp variant: threads per CTA the register file allows for M cells per lane
 constexpr int mw_max_threads(int M) { return M <= 8 ? 512 : 256; }
 
 template <int M, int METHOD, int ARITH, bool MW>
-__global__ void __launch_bounds__(MW ? mw_max_threads(M) : kBlockThreads, MW ? 1 : min_blocks_for(M))
+__global__ void __launch_bounds__(MW ? mw_max_threads(M) : kMaxBlockThreads, MW ? 1 : min_blocks_for(M) / 2)
     k_single_resident(const BatchDev b, const int L, const int cpw) {
   constexpr int ST = (METHOD == CHROM_RK4) ? 3 : 1;
   using Q = Coef<ARITH>;
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(MW ? mw_max_threads(M) : kBlockThreads, MW ? 1
     active = true;
     gmask = 0xffffffffu;
   } else {
-    const uint32_t gw = blockIdx.x * (kBlockThreads / 32) + warp;
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
     const int sub = lane / L;
     p = lane - sub * L;
     col = gw * cpw + sub;
@@ -70,8 +72,9 @@ __global__ void __launch_bounds__(MW ? mw_max_threads(M) : kBlockThreads, MW ? 1
 
   const int cell0 = p * M;
   const int nv = max(0, min(M, (int)nz - cell0));  // real cells on this lane
-  const int p_out = (int)(nz - 1) / M;
-  const int j_out = (int)(nz - 1) - p_out * M;
+  const int det = (int)detector_of(cp.detector_cell, nz);  // where outlet and summary are sampled (default: nz - 1)
+  const int p_out = det / M;
+  const int j_out = det - p_out * M;
   const bool out_lane = active && (p == p_out);
 
   double y[M], u[M], acc[M];
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(MW ? mw_max_threads(M) : kBlockThreads, MW ? 1
 
   auto outlet_value = [&]() -> double {
     double v = y[M - 1];
-    if (j_out != M - 1) {
+    if (j_out != M - 1) {  // (the usual detector - the outlet of a column whose length is a multiple of M - skips this)
 #pragma unroll
       for (int j = 0; j < M - 1; ++j) v = (j == j_out) ? y[j] : v;
     }
@@ -101,32 +104,28 @@ __global__ void __launch_bounds__(MW ? mw_max_threads(M) : kBlockThreads, MW ? 1
   };
 
   // This launch advances steps [s0, s1); s0 > 0 continues a solve from the carried state in y0 (the last chunk
-  // of a one-shot solve is time-sliced so that its outlet series can go back to the host slice by slice; the
-  // host never slices a solve that accumulates the on-device summary).
+  // of a one-shot solve is time-sliced so that its outlet series can go back to the host slice by slice; the raw
+  // sums of the on-device summary are parked in the summary buffer between slices).
   const uint32_t s0 = b.step_begin, s1 = b.step_end;
+  // The running summary lives in shared memory, one slot per column of the CTA, touched by the detector lane only:
+  // seven more doubles per lane would not fit the register file of the widest variants.
+  __shared__ Summ summ_sh[MW ? 1 : (kMaxBlockThreads / 32) * 32];
+  Summ& sm = summ_sh[MW ? 0 : (warp * 32 + lane / L)];
   // step 0 samples (initial condition: rk4.rs:254-255)
-  double v_prev = 0.0, s_area = 0.0, s_mom = 0.0, s_max = 0.0, s_tmax = 0.0;
   if (s0 == 0) {
     const double v0 = outlet_value();
-    v_prev = v0;
-    s_max = v0;
-    if (out_lane && b.outlet) b.outlet[(size_t)col * b.n_out] = v0;
-    if (active && b.snapshots) store_profile(b.snapshots + (size_t)col * b.n_snap * nz);
+    if (out_lane) summ_init(sm, v0);
+    if (out_lane && b.outlet && sample_has_initial(b.out_steps, b.outlet_stride)) b.outlet[(size_t)col * b.n_out] = v0;
+    if (active && b.snapshots && sample_has_initial(b.snap_steps, b.snapshot_stride))
+      store_profile(b.snapshots + (size_t)col * b.n_snap * nz);
+  } else if (out_lane && b.summary) {
+    summ_resume(sm, b.summary + (size_t)col * CHROM_SUMMARY_LEN, outlet_value());
   }
-  uint32_t out_count = b.outlet_stride, snap_count = b.snapshot_stride;
-  uint32_t out_slot = 1, snap_slot = 1;
-  bool done = false;
-  if (s0 > 0) {
-    if (b.outlet_stride) {
-      out_slot = s0 / b.outlet_stride + 1;
-      out_count = b.outlet_stride - s0 % b.outlet_stride;
-    }
-    if (b.snapshot_stride) {
-      snap_slot = s0 / b.snapshot_stride + 1;
-      snap_count = b.snapshot_stride - s0 % b.snapshot_stride;
-    }
-    done = (b.status != nullptr) && (b.status[colc] != 0);  // validate_state already fired in an earlier slice
-  }
+  SampleCursor oc = sample_begin(b.out_steps, b.n_out, b.outlet ? b.outlet_stride : 0u, s0);
+  SampleCursor sc_ = sample_begin(b.snap_steps, b.n_snap, b.snapshots ? b.snapshot_stride : 0u, s0);
+  if (!b.outlet) oc.next = kNoSample;
+  if (!b.snapshots) sc_.next = kNoSample;
+  bool done = (s0 > 0) && (b.status != nullptr) && (b.status[colc] != 0);  // validate_state fired in an earlier slice
 
   double n0 = 0.0, n1 = 0.0, n2 = 0.0;
   n0 = tab[(size_t)s0 * ST];
@@ -203,30 +202,19 @@ __global__ void __launch_bounds__(MW ? mw_max_threads(M) : kBlockThreads, MW ? 1
     }
 
     // ---- samples ------------------------------------------------------------------------
-    const bool want_out = (b.outlet != nullptr) && (--out_count == 0);
+    const uint32_t done_steps = step + 1u;
+    const bool want_out = (done_steps == oc.next);
     if (b.summary != nullptr || want_out) {
       const double v = outlet_value();
       if (want_out) {
-        out_count = b.outlet_stride;
-        if (out_lane) b.outlet[(size_t)col * b.n_out + out_slot] = v;
-        ++out_slot;
+        if (out_lane) b.outlet[(size_t)col * b.n_out + oc.k] = v;
+        sample_advance(oc, b.out_steps, b.outlet_stride);
       }
-      if (b.summary != nullptr && out_lane) {
-        const double t0 = (double)step * dt, t1 = ((double)step + 1.0) * dt;
-        const double w = 0.5 * (t1 - t0);
-        s_area = fma(w, v_prev + v, s_area);
-        s_mom = fma(w, fma(t0, v_prev, t1 * v), s_mom);
-        if (v > s_max) {
-          s_max = v;
-          s_tmax = t1;
-        }
-        v_prev = v;
-      }
+      if (b.summary != nullptr && out_lane) summ_step(sm, v, step, dt);
     }
-    if (b.snapshots != nullptr && --snap_count == 0) {
-      snap_count = b.snapshot_stride;
-      if (active) store_profile(b.snapshots + ((size_t)col * b.n_snap + snap_slot) * nz);
-      ++snap_slot;
+    if (done_steps == sc_.next) {
+      if (active) store_profile(b.snapshots + ((size_t)col * b.n_snap + sc_.k) * nz);
+      sample_advance(sc_, b.snap_steps, b.snapshot_stride);
     }
 
     // ---- validate_state (solver/mod.rs:514-553) ---------------------------------------------------
@@ -270,11 +258,9 @@ __global__ void __launch_bounds__(MW ? mw_max_threads(M) : kBlockThreads, MW ? 1
 
   if (active && b.final_state) store_profile(b.final_state + (size_t)col * nz);
   if (out_lane && b.summary) {
-    double* s = b.summary + (size_t)col * 4;
-    s[0] = s_area;
-    s[1] = (s_area != 0.0) ? s_mom / s_area : 0.0;
-    s[2] = s_max;
-    s[3] = s_tmax;
+    double* o = b.summary + (size_t)col * CHROM_SUMMARY_LEN;
+    if (s1 >= steps) summ_store(o, sm);
+    else summ_park(o, sm);  // a later slice of the same solve resumes from the raw sums
   }
 }
 
@@ -339,14 +325,24 @@ bool single_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std:
     if (why) *why = "nz exceeds the register-resident capacity (8192 cells per CTA)";
     return false;
   }
-  char buf[160];
+  char buf[360];
   const char* force = getenv("CHROM_FORCE_M");  // experiments only
   const uint64_t fill_warps = (uint64_t)sm_count * 8u;
 
   // ---- candidate 1: a single warp per column (nz <= 1024) ------------------------------------------------
-  // Maximise (fraction of lane-slots doing real cells) x (measured efficiency of the chunk size); when the
-  // batch cannot fill the machine prefer short chunks (more lanes in flight per column).
-  double sw_score = -1.0;
+  // Cost model, in "cells a lane steps through per time step" on the busiest SM sub-partition (the kernel is bound
+  // by the FP64 pipe of its sub-partition; measured on B200, profiles/r2_single_shapes_8192.jsonl):
+  //   warps = ceil(n_cols / cpw);  a sub-partition holds wps(M) resident warps (register file), the machine
+  //   slots = 4 SMs sub-partitions;  full waves cost wps * M / eff_m each, the last partial wave ceil(rest / slots) *
+  //   M / eff_m.  eff_m = measured fraction of the FP64 peak at a perfect fit: flat 0.69-0.72 for 6 <= M <= 25, lower
+  //   for very short chunks (per-lane overhead) and for M >= 28 (255 registers).
+  // For a batch of many waves this is the old "lane utilisation x eff_m" rule; for a batch that cannot fill the machine
+  // it sees the quantisation (8192 columns of nz = 100: M = 25 puts 2 warps on 432 of 592 sub-partitions and 1 on
+  // the rest, 24.7 ms instead of the 20.6 ms of a perfect spread), and for a handful of columns the shortest chunk.
+  auto eff_of = [](int M) { return M < 6 ? 0.645 : (M == 12 || M == 25) ? 0.72 : M <= 25 ? 0.70 : M == 28 ? 0.675 : 0.65; };
+  auto wps_of = [](int M) { return min_blocks_for(M) * (kBlockThreads / 32) / 4; };
+  const uint64_t slots = (uint64_t)sm_count * 4u;
+  double sw_cost = 1e300;
   int swM = 0, swL = 0, swCpw = 0;
   bool latency_bound = false;
   if (nz <= 32u * 32u) {
@@ -355,25 +351,45 @@ bool single_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std:
       const int L = (int)((nz + M - 1) / M);
       if (L > 32) continue;
       const int cpw = 32 / L;
-      const double eff = (double)nz * cpw / (32.0 * M);
-      const uint64_t warps = (b.n_cols + cpw - 1) / cpw;
-      // measured fraction of FP64 peak at a perfect fit (32 lanes per column, gpurun_out/single_shapes_*.jsonl):
-      // flat 0.69-0.72 for 6 <= M <= 25, lower for very short chunks (per-lane overhead) and for M >= 28
-      // (255 registers: 8 warps per SM)
-      const double eff_m = M < 6 ? 0.645 : (M == 12 || M == 25) ? 0.72 : M <= 25 ? 0.70 : M == 28 ? 0.675 : 0.65;
-      double score = eff * eff_m;
-      if (warps < fill_warps) {  // latency-bound batch: shortest critical path wins
-        score = eff / M;
-        latency_bound = true;
-      }
-      if (score > sw_score) {
-        sw_score = score;
+      const uint64_t warps = ((uint64_t)b.n_cols + cpw - 1) / cpw;
+      const uint64_t cap = slots * (uint64_t)wps_of(M);
+      const uint64_t full = warps / cap, rest = warps % cap;
+      const double cost = ((double)full * wps_of(M) + (double)((rest + slots - 1) / slots)) * M / eff_of(M);
+      if (cost < sw_cost) {
+        sw_cost = cost;
         swM = M;
         swL = L;
         swCpw = cpw;
+        latency_bound = warps < fill_warps / 2;
       }
     }
   }
+  // A sub-wave batch: two launches with different chunk sizes, side by side (one warp of each per sub-partition).
+  // 8192 columns of nz = 100: 4736 columns at M = 25 (8 per warp) + 3456 at M = 20 (6 per warp) = 45 cells per lane
+  // instead of 50; measured 22.8 ms against 24.7 ms (scripts/split_experiment.py).
+  int spA = 0, spB = 0;
+  double sp_cost = 1e300;
+  if (swM && !force && !getenv("CHROM_NO_SPLIT") && nz <= 32u * 32u) {
+    const uint64_t warps1 = ((uint64_t)b.n_cols + swCpw - 1) / swCpw;
+    if (warps1 > slots && warps1 <= 2 * slots) {  // the single launch puts 2 warps on some sub-partitions, 1 on others
+      for (int MA : kM)
+        for (int MB : kM) {
+          if (MB > MA || MA < 11 || MB < 11) continue;  // 255 / 168 registers: one CTA of each per SM
+          const int LA = (int)((nz + MA - 1) / MA), LB = (int)((nz + MB - 1) / MB);
+          if (LA > 32 || LB > 32) continue;
+          const uint64_t capA = slots * (uint64_t)(32 / LA), capB = slots * (uint64_t)(32 / LB);
+          if (capA + capB < b.n_cols || capA >= b.n_cols) continue;
+          const double cost = MA / eff_of(MA) + MB / eff_of(MB);
+          if (cost < sp_cost) {
+            sp_cost = cost;
+            spA = MA;
+            spB = MB;
+          }
+        }
+      if (!(sp_cost < 0.96 * sw_cost)) spA = spB = 0;
+    }
+  }
+  const double sw_score = swM ? 1.0 / sw_cost : -1.0;
 
   // ---- candidate 2: several warps per column, one CTA per column (nz > 512) ------------------------------
   // score = (fraction of lane-slots doing real cells) x (measured efficiency of the chunk size at a perfect fit)
@@ -395,7 +411,7 @@ bool single_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std:
       }
       const int wt = W * ctas;
       const double balance = (double)wt / (4.0 * ((wt + 3) / 4));
-      const double score = (double)nz / ((double)W * 32.0 * M) * eff_m * balance;
+      const double score = (double)nz / ((double)W * 32.0 * M) * eff_m * balance;  // fraction of the FP64 peak
       if (score >= mw_score) {
         mw_score = score;
         mwM = M;
@@ -404,7 +420,10 @@ bool single_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std:
     }
   }
 
-  if (swM && (sw_score >= mw_score || !mwM)) {
+  // the single-warp candidate as a fraction of the FP64 peak too: useful cell-steps per lane-slot over its cost
+  const double sw_frac = swM ? ((double)b.n_cols * nz / ((double)slots * 32.0)) / sw_cost : -1.0;
+  (void)sw_score;
+  if (swM && (sw_frac >= mw_score || !mwM || b.n_cols < (uint32_t)sm_count)) {
     const uint64_t warps = ((uint64_t)b.n_cols + swCpw - 1) / swCpw;
     g->kind = 1;
     g->M = swM;
@@ -419,6 +438,23 @@ bool single_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std:
              swM, b.method == CHROM_RK4 ? "RK4" : "Euler", arith_name(b.arith),
              swL, swCpw, g->grid.x, kBlockThreads);
     g->name = buf;
+    if (spA) {  // two launches side by side: 128-thread CTAs, one warp per sub-partition each
+      g->M = spA;
+      g->L = (int)((nz + spA - 1) / spA);
+      g->cpw = 32 / g->L;
+      g->M2 = spB;
+      g->L2 = (int)((nz + spB - 1) / spB);
+      g->cpw2 = 32 / g->L2;
+      g->cols_first = (uint32_t)std::min<uint64_t>(b.n_cols, slots * (uint64_t)g->cpw);
+      g->block = dim3(kMaxBlockThreads);
+      g->cols_per_wave = b.n_cols;  // one wave by construction: never chunked
+      snprintf(buf, sizeof buf,
+               "single_resident<M=%d+%d,%s,%s> split launch: %u columns at %d cells/lane (%d cols/warp) + %u at %d (%d cols/warp), "
+               "one warp of each per SM sub-partition, block=%d",
+               spA, spB, b.method == CHROM_RK4 ? "RK4" : "Euler", arith_name(b.arith), g->cols_first, spA, g->cpw,
+               b.n_cols - g->cols_first, spB, g->cpw2, kMaxBlockThreads);
+      g->name = buf;
+    }
     return true;
   }
   if (mwM == 0) return false;
@@ -438,9 +474,61 @@ bool single_resident_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std:
   return true;
 }
 
+namespace {
+// columns [c0, c0 + cnt) of a single-species batch: every per-column pointer offset
+BatchDev offset_cols(BatchDev b, uint64_t c0, uint64_t cnt) {
+  const size_t nz = b.nz;
+  if (b.scols) b.scols += c0;
+  if (b.y0) b.y0 += c0 * nz;
+  if (b.outlet) b.outlet += c0 * b.n_out;
+  if (b.snapshots) b.snapshots += c0 * b.n_snap * nz;
+  if (b.final_state) b.final_state += c0 * nz;
+  if (b.summary) b.summary += c0 * CHROM_SUMMARY_LEN;
+  if (b.status) b.status += c0;
+  b.n_cols = (uint32_t)cnt;
+  return b;
+}
+cudaStream_t side_stream() {  // one helper stream per device, created on first use
+  static cudaStream_t streams[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    streams[dev] = nullptr;
+  }
+  return streams[dev];
+}
+}  // namespace
+
 cudaError_t single_resident_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s) {
   kern_t k = lookup(g.M, g.kind == 2, b.method, b.arith);
   if (!k) return cudaErrorInvalidValue;
+  if (g.kind == 1 && g.M2 > 0 && b.n_cols > g.cols_first) {
+    // split launch (see single_resident_choose): the first cols_first columns at M cells per lane on `s`, the rest
+    // at M2 on a side stream that forks from and joins back into `s`
+    kern_t k2 = lookup(g.M2, false, b.method, b.arith);
+    cudaStream_t s2 = side_stream();
+    if (!k2 || !s2) return cudaErrorInvalidValue;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaError_t e = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(fork, s);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s2, fork, 0);
+    if (e == cudaSuccess) {
+      const int wpb = kMaxBlockThreads / 32;
+      const BatchDev ba = offset_cols(b, 0, g.cols_first), bb = offset_cols(b, g.cols_first, b.n_cols - g.cols_first);
+      const uint64_t wa = ((uint64_t)ba.n_cols + g.cpw - 1) / g.cpw, wb = ((uint64_t)bb.n_cols + g.cpw2 - 1) / g.cpw2;
+      k<<<dim3((unsigned)((wa + wpb - 1) / wpb)), dim3(kMaxBlockThreads), 0, s>>>(ba, g.L, g.cpw);
+      k2<<<dim3((unsigned)((wb + wpb - 1) / wpb)), dim3(kMaxBlockThreads), 0, s2>>>(bb, g.L2, g.cpw2);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(join, s2);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, join, 0);
+    if (fork) cudaEventDestroy(fork);
+    if (join) cudaEventDestroy(join);
+    return e;
+  }
   // grid from b.n_cols (a chunk of the planned batch may be launched on its own)
   dim3 grid = g.grid;
   if (g.kind == 1) {
@@ -449,7 +537,7 @@ cudaError_t single_resident_launch(const BatchDev& b, const LaunchGeom& g, cudaS
   } else {
     grid = dim3(b.n_cols);
   }
-  k<<<grid, g.block, g.smem, s>>>(b, g.L, g.cpw);
+  k<<<grid, g.kind == 1 ? dim3(kBlockThreads) : g.block, g.smem, s>>>(b, g.L, g.cpw);
   return cudaGetLastError();
 }
 

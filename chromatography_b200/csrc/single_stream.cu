@@ -98,8 +98,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32)
   const int j_lo = min(kM, max(0, first_valid - local0));
   const int j_hi = (int)min((long long)kM, max(0ll, (long long)nz - cell0));
   const bool full_lane = (j_lo == 0) && (j_hi == kM);
-  const long long oj = (long long)nz - 1 - cell0;
-  const int out_j = (b.outlet != nullptr && oj >= (long long)j_lo && oj < (long long)j_hi) ? (int)oj : -1;
+  // the detector cell (default: the outlet) lives on exactly one lane of one tile
+  const long long oj = (long long)detector_of(b.scols[col].detector_cell, nz) - cell0;
+  const int out_j = ((b.outlet != nullptr || b.series != nullptr) && oj >= (long long)j_lo && oj < (long long)j_hi) ? (int)oj : -1;
 
   bool bad = false, has_nan = false;
   uint32_t bad_step = 0;
@@ -160,11 +161,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32)
       for (int j = 0; j < kM; ++j)
         if (j >= j_lo && j < j_hi) sub_bad |= hi_nonfinite(abs_hi(y[j]));
     }
-    if (out_j >= 0 && ((out_mask >> f) & 1u)) {  // the one lane that holds cell nz-1
+    if (out_j >= 0 && (b.series != nullptr || ((out_mask >> f) & 1u))) {  // the one lane that holds the detector cell
       double v = y[0];
 #pragma unroll
       for (int j = 1; j < kM; ++j) v = (out_j == j) ? y[j] : v;
-      b.outlet[(size_t)col * b.n_out + out_slot0 + (uint32_t)__popc(out_mask & ((1u << f) - 1u))] = v;
+      if ((out_mask >> f) & 1u)
+        b.outlet[(size_t)col * b.n_out + out_slot0 + (uint32_t)__popc(out_mask & ((1u << f) - 1u))] = v;
+      if (b.series != nullptr) b.series[(size_t)col * (b.steps + 1) + done_steps] = v;  // full rate, for the summary
     }
     if (sub_bad && !bad) {  // remember the FIRST bad sub-step of this lane (rare: the NaN scan lives here)
       bool sub_nan = false;
@@ -202,9 +205,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32)
   }
 }
 
-// After the last step: status codes -> the ABI's signed convention, summaries from the outlet series.
-__global__ void k_stream_finalize(const BatchDev b, const unsigned long long* __restrict__ code,
-                                  const double* __restrict__ full_outlet /* [n_cols][steps+1] or null */) {
+// After the last step: status codes -> the ABI's signed convention, summaries from the full-rate detector series.
+__global__ void k_stream_finalize(const BatchDev b, const unsigned long long* __restrict__ code) {
   const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= b.n_cols) return;
   if (b.status) {
@@ -212,27 +214,22 @@ __global__ void k_stream_finalize(const BatchDev b, const unsigned long long* __
     const long long s = (long long)(c >> 1);
     b.status[col] = (c == ~0ull) ? 0ll : ((c & 1ull) ? -s : s);
   }
-  if (b.summary && full_outlet) {
-    const double* o = full_outlet + (size_t)col * (b.steps + 1);
-    double area = 0.0, mom = 0.0, vmax = o[0], tmax = 0.0, vp = o[0];
-    for (uint32_t st = 0; st < b.steps; ++st) {
-      const double v = o[st + 1];
-      const double t0 = (double)st * b.dt, t1 = ((double)st + 1.0) * b.dt;
-      const double w = 0.5 * (t1 - t0);
-      area = fma(w, vp + v, area);
-      mom = fma(w, fma(t0, vp, t1 * v), mom);
-      if (v > vmax) {
-        vmax = v;
-        tmax = t1;
-      }
-      vp = v;
-    }
-    double* sm = b.summary + (size_t)col * 4;
-    sm[0] = area;
-    sm[1] = (area != 0.0) ? mom / area : 0.0;
-    sm[2] = vmax;
-    sm[3] = tmax;
+  if (b.summary && b.series) {
+    const double* o = b.series + (size_t)col * (b.steps + 1);
+    Summ sm;
+    summ_init(sm, o[0]);
+    for (uint32_t st = 0; st < b.steps; ++st) summ_step(sm, o[st + 1], st, b.dt);
+    summ_store(b.summary + (size_t)col * CHROM_SUMMARY_LEN, sm);
   }
+}
+
+// Sample slot 0 (the initial state at the detector cell) of the outlet buffer and of the full-rate series.
+__global__ void k_stream_sample0(const BatchDev b, const double* __restrict__ state, int to_outlet) {
+  const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= b.n_cols) return;
+  const double v = state[(size_t)col * b.nz + detector_of(b.scols[col].detector_cell, b.nz)];
+  if (to_outlet) b.outlet[(size_t)col * b.n_out] = v;
+  if (b.series) b.series[(size_t)col * (b.steps + 1)] = v;
 }
 
 __global__ void k_stream_init(const BatchDev b, double* __restrict__ ping, unsigned long long* __restrict__ code) {
@@ -282,7 +279,10 @@ skern_t pick_stream(int method, int arith, int fuse, int m) {
 int stream_fuse(const BatchDev& b) {
   int f = 8;
   if (const char* e = getenv("CHROM_STREAM_FUSE")) f = atoi(e) >= 8 ? 8 : (atoi(e) >= 4 ? 4 : (atoi(e) >= 2 ? 2 : 1));
-  while (f > 1 && b.snapshots && b.snapshot_stride && (b.snapshot_stride % f) != 0) f /= 2;
+  while (f > 1 && b.snapshots && !b.h_snap_steps && b.snapshot_stride && (b.snapshot_stride % f) != 0) f /= 2;
+  if (b.snapshots && b.h_snap_steps)  // an explicit list: every listed step must fall on a launch boundary
+    for (uint32_t k = 0; k < b.n_snap; ++k)
+      while (f > 1 && (b.h_snap_steps[k] % (uint32_t)f) != 0u && b.h_snap_steps[k] != b.steps) f /= 2;
   while (f > 1 && (uint32_t)f > b.steps) f /= 2;
   return f;
 }
@@ -320,7 +320,7 @@ bool single_stream_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::s
   g->block = dim3(kWarps * 32);
   g->grid = dim3((tiles + kWarps - 1) / kWarps, b.n_cols);
   g->smem = 0;
-  g->launches_per_execute = ((uint64_t)b.steps + fuse - 1) / fuse + 3;
+  g->launches_per_execute = ((uint64_t)b.steps + fuse - 1) / fuse + 4;  // + init, coefficients, sample 0, finalize
   char buf[240];
   snprintf(buf, sizeof buf,
            "single_stream<M=%d,%s,%s> tiles/col=%d halo=%d grid=(%u,%u) block=%d, %d fused step(s) per launch, CUDA graph",
@@ -332,7 +332,8 @@ bool single_stream_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::s
 }
 
 // b.ping: [n_cols][nz]; b.pong: [n_cols][nz] followed by n_cols 64-bit status codes and n_cols
-// coefficient slots (the caller allocates n_cols*(nz + 1 + single_stream_extra_doubles()) doubles).  Summaries need the full-rate outlet: b.outlet with stride 1.
+// coefficient slots (the caller allocates n_cols*(nz + 1 + single_stream_extra_doubles()) doubles).  A summary needs
+// the full-rate detector series b.series [n_cols][steps + 1] (device scratch, allocated by the caller).
 
 cudaError_t single_stream_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s) {
   const int fuse = g.cpw > 0 ? g.cpw : 1;
@@ -348,41 +349,42 @@ cudaError_t single_stream_launch(const BatchDev& b, const LaunchGeom& g, cudaStr
   }
   double* src = b.ping;
   double* dst = b.pong;
-  if (b.outlet) {  // slot 0: the outlet of the initial state
-    for (uint32_t c = 0; c < b.n_cols; ++c) {
-      cudaError_t e = cudaMemcpyAsync(b.outlet + (size_t)c * b.n_out, src + (size_t)c * b.nz + b.nz - 1, sizeof(double),
-                                      cudaMemcpyDeviceToDevice, s);
-      if (e != cudaSuccess) return e;
-    }
-  }
-  auto snapshot = [&](const double* state, uint32_t slot) -> cudaError_t {
-    for (uint32_t c = 0; c < b.n_cols; ++c) {
-      cudaError_t e = cudaMemcpyAsync(b.snapshots + ((size_t)c * b.n_snap + slot) * b.nz, state + (size_t)c * b.nz,
-                                      (size_t)b.nz * sizeof(double), cudaMemcpyDeviceToDevice, s);
-      if (e != cudaSuccess) return e;
-    }
-    return cudaSuccess;
+  const dim3 cgrid((b.n_cols + 127) / 128), cblock(128);
+  // sample schedules, walked on the host: which sub-steps of a launch sample the outlet (and into which slot), which
+  // launch boundaries take a snapshot
+  SampleCursor oc = sample_begin(b.h_out_steps, b.n_out, b.outlet ? b.outlet_stride : 0u, 0u);
+  SampleCursor sc = sample_begin(b.h_snap_steps, b.n_snap, b.snapshots ? b.snapshot_stride : 0u, 0u);
+  if (!b.outlet) oc.next = kNoSample;
+  if (!b.snapshots) sc.next = kNoSample;
+  const bool out0 = b.outlet && sample_has_initial(b.h_out_steps, b.outlet_stride);
+  k_stream_sample0<<<cgrid, cblock, 0, s>>>(b, src, out0 ? 1 : 0);
+  auto snapshot = [&](const double* state, uint32_t slot) -> cudaError_t {  // one strided copy for the whole batch
+    return cudaMemcpy2DAsync(b.snapshots + (size_t)slot * b.nz, (size_t)b.n_snap * b.nz * sizeof(double), state,
+                             (size_t)b.nz * sizeof(double), (size_t)b.nz * sizeof(double), b.n_cols,
+                             cudaMemcpyDeviceToDevice, s);
   };
-  if (b.snapshots) {
+  if (b.snapshots && sample_has_initial(b.h_snap_steps, b.snapshot_stride)) {
     cudaError_t e = snapshot(src, 0);
     if (e != cudaSuccess) return e;
   }
   for (uint32_t step = 0; step < b.steps; step += (uint32_t)fuse) {
     const int nsub = (int)std::min<uint32_t>((uint32_t)fuse, b.steps - step);
     uint32_t out_mask = 0u, out_slot0 = 0u;  // sub-steps of this launch that sample the outlet, first slot
-    if (b.outlet && b.outlet_stride)
-      for (int f = 0; f < nsub; ++f) {
-        const uint64_t ds = (uint64_t)step + (uint64_t)f + 1u;
-        if (ds % b.outlet_stride == 0) {
-          if (!out_mask) out_slot0 = (uint32_t)(ds / b.outlet_stride);
-          out_mask |= 1u << f;
-        }
+    for (int f = 0; f < nsub; ++f) {
+      const uint32_t ds = step + (uint32_t)f + 1u;
+      if (ds == oc.next) {
+        if (!out_mask) out_slot0 = oc.k;
+        out_mask |= 1u << f;
+        sample_advance(oc, b.h_out_steps, b.outlet_stride);
       }
+    }
     k<<<g.grid, g.block, 0, s>>>(b, src, dst, step, code, nsub, g.warps_per_col, out_mask, out_slot0);
     const uint32_t done = step + (uint32_t)nsub;
-    if (b.snapshots && b.snapshot_stride && (done % b.snapshot_stride == 0)) {
-      cudaError_t e = snapshot(dst, done / b.snapshot_stride);
+    while (sc.next != kNoSample && sc.next < done) sample_advance(sc, b.h_snap_steps, b.snapshot_stride);  // not on a boundary
+    if (done == sc.next) {
+      cudaError_t e = snapshot(dst, sc.k);
       if (e != cudaSuccess) return e;
+      sample_advance(sc, b.h_snap_steps, b.snapshot_stride);
     }
     double* t = src;
     src = dst;
@@ -392,8 +394,7 @@ cudaError_t single_stream_launch(const BatchDev& b, const LaunchGeom& g, cudaStr
     cudaError_t e = cudaMemcpyAsync(b.final_state, src, plane * sizeof(double), cudaMemcpyDeviceToDevice, s);
     if (e != cudaSuccess) return e;
   }
-  const double* full = (b.outlet && b.outlet_stride == 1) ? b.outlet : nullptr;
-  k_stream_finalize<<<(b.n_cols + 127) / 128, 128, 0, s>>>(b, code, full);
+  k_stream_finalize<<<cgrid, cblock, 0, s>>>(b, code);
   return cudaGetLastError();
 }
 

@@ -591,7 +591,7 @@ Result<std::vector<Result<SimulationResult>>> CudaSolverBase::solve_batch_on(std
   PinnedBuf<double> outlet, snaps, final_state, summary;
   PinnedBuf<std::int64_t> status;
   if (!outlet.alloc(n_cols * n * n_out) || !snaps.alloc(n_cols * n_snap * n * nz) || !final_state.alloc(n_cols * n * nz) ||
-      !summary.alloc(opt.summary ? n_cols * n * 4 : 0) || !status.alloc(n_cols))
+      !summary.alloc(opt.summary ? n_cols * n * CHROM_SUMMARY_LEN : 0) || !status.alloc(n_cols))
     return Err("chrom_cuda_host_alloc failed: not enough page-locked host memory for the requested outputs "
                "(lower BatchOptions::snapshot_stride / outlet_stride)");
 
@@ -654,8 +654,8 @@ Result<std::vector<Result<SimulationResult>>> CudaSolverBase::solve_batch_on(std
     }
     if (opt.summary)
       for (std::size_t sp = 0; sp < n; ++sp) {
-        const double* q = summary.get() + (k * n + sp) * 4;
-        r.summary.emplace_back(q, q + 4);
+        const double* q = summary.get() + (k * n + sp) * CHROM_SUMMARY_LEN;
+        r.summary.emplace_back(q, q + CHROM_SUMMARY_LEN);
       }
     results.emplace_back(std::move(r));
     ++k;

@@ -230,9 +230,36 @@ def status_message(status: int):
 
 
 def make_cfg(method, total_time, time_steps, n_points, n_species=1, outlet_stride=1, snapshot_stride=0,
-             arith=_ffi.ARITH_FAST) -> _ffi.RunCfg:
-    return _ffi.RunCfg(method, arith, float(total_time), int(time_steps), int(n_points), int(n_species),
-                       int(outlet_stride), int(snapshot_stride))
+             arith=_ffi.ARITH_FAST, outlet_steps=None, snapshot_steps=None) -> _ffi.RunCfg:
+    """outlet_steps / snapshot_steps: explicit strictly increasing step lists (what sample_indices(time_steps + 1, n)
+    returns, physics/traits.rs:1010-1023); a list replaces the corresponding stride."""
+    cfg = _ffi.RunCfg(method, arith, float(total_time), int(time_steps), int(n_points), int(n_species),
+                      int(outlet_stride), int(snapshot_stride))
+    keep = []
+    for name, steps in (("outlet", outlet_steps), ("snapshot", snapshot_steps)):
+        if steps is None:
+            continue
+        arr = np.ascontiguousarray(steps, dtype=np.uint64)
+        keep.append(arr)  # the struct only borrows the memory: the array lives as long as the cfg object
+        setattr(cfg, f"{name}_steps", arr.ctypes.data_as(C.POINTER(C.c_uint64)))
+        setattr(cfg, f"n_{name}_steps", arr.size)
+    cfg._keepalive = keep
+    return cfg
+
+
+def sample_indices(total: int, n: int | None) -> np.ndarray:
+    """sample_indices(total, n) of the reference (physics/traits.rs:1010-1023); n None / 0 = every index."""
+    lib = _ffi.lib()
+    n = int(n or 0)
+    count = lib.chrom_cuda_sample_indices(int(total), n, None, 0)
+    out = np.zeros(count, dtype=np.uint64)
+    lib.chrom_cuda_sample_indices(int(total), n, out.ctypes.data_as(C.POINTER(C.c_uint64)), count)
+    return out
+
+
+def node_index(position: float, column_length: float, n_points: int) -> int:
+    """Detector::node_index (domain/detector.rs:285-290): the grid node closest to a position in metres."""
+    return int(_ffi.lib().chrom_cuda_node_index(float(position), float(column_length), int(n_points)))
 
 
 class _TableSet:
@@ -261,7 +288,8 @@ def pack_single(models, method, total_time, time_steps):
     ts = _TableSet(method, total_time, time_steps)
     cols = (_ffi.SingleCol * len(models))()
     for i, m in enumerate(models):
-        cols[i] = _ffi.SingleCol(m.lambda_, m.langmuir_k, m.port_number, m.fe, m.ue, m.dz, ts.add(m.injection), 0)
+        cols[i] = _ffi.SingleCol(m.lambda_, m.langmuir_k, m.port_number, m.fe, m.ue, m.dz, ts.add(m.injection),
+                                 int(getattr(m, "detector_cell", 0)))  # 0 = outlet, k = cell k - 1
     return cols, ts.array()
 
 
@@ -273,7 +301,7 @@ def pack_multi(models, method, total_time, time_steps):
     for i, m in enumerate(models):
         if m.n_species() != n:
             raise SolverError("all columns of a batch must have the same number of species")
-        cols[i] = _ffi.MultiCol(m.fe, m.ue, m.dz, m.stationary_fraction, i * n, 0)
+        cols[i] = _ffi.MultiCol(m.fe, m.ue, m.dz, m.stationary_fraction, i * n, int(getattr(m, "detector_cell", 0)))
         for k, s in enumerate(m.species):
             species[i * n + k] = _ffi.Species(s.lambda_, s.langmuir_k, s.port_number, ts.add(s.injection))
     return cols, species, ts.array()
@@ -284,7 +312,7 @@ class BatchResult:
     outlet: np.ndarray | None        # [n_cols, n_out] / [n_cols, n_species, n_out]
     snapshots: np.ndarray | None     # [n_cols, n_snap, nz] / [n_cols, n_snap, n_species, nz]
     final_state: np.ndarray | None   # [n_cols, nz] / [n_cols, n_species, nz]
-    summary: np.ndarray | None       # [n_cols, 4] / [n_cols, n_species, 4]
+    summary: np.ndarray | None       # [n_cols, 6] / [n_cols, n_species, 6]: area, first moment, max, t_max, sigma, min
     status: np.ndarray               # [n_cols] int64
     timing: dict
 
@@ -293,12 +321,12 @@ def solve_single_batch(ctx: Context, cfg: _ffi.RunCfg, cols, tables: np.ndarray,
                        want_snapshots=False, want_final=True, want_summary=False) -> BatchResult:
     lib = _ffi.lib()
     n_cols, nz = len(cols), cfg.n_points
-    n_out = lib.chrom_cuda_n_samples(cfg.time_steps, cfg.outlet_stride)
-    n_snap = lib.chrom_cuda_n_samples(cfg.time_steps, cfg.snapshot_stride)
+    n_out = lib.chrom_cuda_cfg_n_out(C.byref(cfg))
+    n_snap = lib.chrom_cuda_cfg_n_snap(C.byref(cfg))
     outlet = np.empty((n_cols, n_out)) if (want_outlet and n_out) else None
     snaps = np.empty((n_cols, n_snap, nz)) if (want_snapshots and n_snap) else None
     final = np.empty((n_cols, nz)) if want_final else None
-    summ = np.empty((n_cols, 4)) if want_summary else None
+    summ = np.empty((n_cols, _ffi.SUMMARY_LEN)) if want_summary else None
     status = np.zeros(n_cols, dtype=np.int64)
     y0c = None if y0 is None else np.ascontiguousarray(y0, dtype=np.float64).reshape(n_cols, nz)
     tables = np.ascontiguousarray(tables, dtype=np.float64)
@@ -312,12 +340,12 @@ def solve_multi_batch(ctx: Context, cfg: _ffi.RunCfg, cols, species, tables: np.
                       want_snapshots=False, want_final=True, want_summary=False) -> BatchResult:
     lib = _ffi.lib()
     n_cols, nz, n = len(cols), cfg.n_points, cfg.n_species
-    n_out = lib.chrom_cuda_n_samples(cfg.time_steps, cfg.outlet_stride)
-    n_snap = lib.chrom_cuda_n_samples(cfg.time_steps, cfg.snapshot_stride)
+    n_out = lib.chrom_cuda_cfg_n_out(C.byref(cfg))
+    n_snap = lib.chrom_cuda_cfg_n_snap(C.byref(cfg))
     outlet = np.empty((n_cols, n, n_out)) if (want_outlet and n_out) else None
     snaps = np.empty((n_cols, n_snap, n, nz)) if (want_snapshots and n_snap) else None
     final = np.empty((n_cols, n, nz)) if want_final else None
-    summ = np.empty((n_cols, n, 4)) if want_summary else None
+    summ = np.empty((n_cols, n, _ffi.SUMMARY_LEN)) if want_summary else None
     status = np.zeros(n_cols, dtype=np.int64)
     y0c = None if y0 is None else np.ascontiguousarray(y0, dtype=np.float64).reshape(n_cols, n, nz)
     tables = np.ascontiguousarray(tables, dtype=np.float64)
@@ -359,17 +387,25 @@ class Plan:
     def download(self) -> BatchResult:
         lib = _ffi.lib()
         cfg, n_cols, nz, n = self.cfg, self.n_cols, self.cfg.n_points, self.cfg.n_species
-        n_out = lib.chrom_cuda_n_samples(cfg.time_steps, cfg.outlet_stride)
-        n_snap = lib.chrom_cuda_n_samples(cfg.time_steps, cfg.snapshot_stride)
+        n_out = lib.chrom_cuda_cfg_n_out(C.byref(cfg))
+        n_snap = lib.chrom_cuda_cfg_n_snap(C.byref(cfg))
         sp = (n,) if self.multi else ()
         outlet = np.empty((n_cols,) + sp + (n_out,)) if (self.want & _ffi.WANT_OUTLET and n_out) else None
         snaps = np.empty((n_cols, n_snap) + sp + (nz,)) if (self.want & _ffi.WANT_SNAPSHOTS and n_snap) else None
         final = np.empty((n_cols,) + sp + (nz,)) if self.want & _ffi.WANT_FINAL else None
-        summ = np.empty((n_cols,) + sp + (4,)) if self.want & _ffi.WANT_SUMMARY else None
+        summ = np.empty((n_cols,) + sp + (_ffi.SUMMARY_LEN,)) if self.want & _ffi.WANT_SUMMARY else None
         status = np.zeros(n_cols, dtype=np.int64)
         self.ctx.check(lib.chrom_cuda_plan_download(self._h, _dp(outlet), _dp(snaps), _dp(final), _dp(summ),
                                                     status.ctypes.data_as(C.POINTER(C.c_int64))))
         return BatchResult(outlet, snaps, final, summ, status, self.ctx.timing())
+
+    def rsf(self, other: "Plan") -> np.ndarray:
+        """Surface resolution Rsf (validation/dissimilarity.rs:173-203) between this plan's outlet series and
+        `other`'s, per column (and species), computed on the device: neither series moves to the host."""
+        sp = (self.cfg.n_species,) if self.multi else ()
+        out = np.empty((self.n_cols,) + sp)
+        self.ctx.check(_ffi.lib().chrom_cuda_plan_rsf(self._h, other._h, _dp(out)))
+        return out
 
     def close(self):
         if getattr(self, "_h", None):

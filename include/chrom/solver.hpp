@@ -149,7 +149,7 @@ struct SimulationResult {
   // Extras the device produces anyway (not in the reference's struct; empty unless requested):
   std::vector<std::vector<double>> outlet;   // [species][n_out]: last cell at steps 0, k, 2k, ...
   std::vector<double> outlet_time_points;    // the time of each outlet sample
-  std::vector<std::vector<double>> summary;  // [species][4]: trapezoid area, first moment, max, time of max
+  std::vector<std::vector<double>> summary;  // [species][CHROM_SUMMARY_LEN]: trapezoid area, first moment, max, time of max, sigma, min
   std::vector<std::size_t> trajectory_steps; // the step index of each state in state_trajectory
 
   SimulationResult() = default;
@@ -205,7 +205,7 @@ class CudaContext {
 struct BatchOptions {
   std::size_t snapshot_stride = 1;  // 1 = the reference's full state_trajectory; k = every k-th step; 0 = none
   std::size_t outlet_stride = 1;    // outlet series sampling; 0 = none
-  bool summary = true;              // on-device area / first moment / max / time of max of the outlet
+  bool summary = true;              // on-device area / first moment / max / time of max / sigma / min of the outlet
 };
 
 class CudaSolverBase : public Solver {

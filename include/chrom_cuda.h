@@ -14,6 +14,11 @@
  *   chrom_cuda_status_message       the Err(String) texts of src/solver/mod.rs:527-548
  *   chrom_cuda_validate_cfg         SolverType::validate  src/solver/traits.rs:172-185
  *   chrom_cuda_time_points          time_points of SimulationResult  rk4.rs:254,327
+ *   chrom_cuda_sample_indices       sample_indices  src/physics/traits.rs:1010-1023 (the export / plot sampling rule)
+ *   chrom_cuda_node_index           Detector::node_index  src/domain/detector.rs:285-290
+ *   summary[]                       trapezoid / first_moment / peak_sigma of the validation suite
+ *                                   validation/dissimilarity.rs:81-88, validation/main.rs:190-206
+ *   chrom_cuda_plan_rsf             rsf  validation/dissimilarity.rs:173-203 (two series on one time grid)
  *   plan_* functions                no reference counterpart: keep a batch resident in HBM between calls
  *
  * Conventions: every function returns CHROM_OK (0) or a negative CHROM_ERR_*; the text of the last
@@ -69,15 +74,16 @@ typedef struct chrom_cuda_plan chrom_cuda_plan;
  * the model file and never recomputes them: src/config/model.rs:111-148). */
 typedef struct {
   double lambda, langmuir_k, port_number, fe, ue, dz;
-  uint32_t inj_table; /* index into inj_tables */
-  uint32_t _reserved;
+  uint32_t inj_table;     /* index into inj_tables */
+  uint32_t detector_cell; /* where "outlet" and "summary" are sampled: 0 = the column outlet (last cell, the reference's
+                             default Detector::outlet()); k > 0 = cell k - 1 (Detector::node_index, detector.rs:285) */
 } chrom_single_col;
 
 /* One LangmuirMulti column; its species are species[species_off .. species_off + n_species). */
 typedef struct {
   double fe, ue, dz, stationary_fraction;
   uint32_t species_off;
-  uint32_t _reserved;
+  uint32_t detector_cell; /* as in chrom_single_col */
 } chrom_multi_col;
 
 typedef struct {
@@ -95,7 +101,22 @@ typedef struct {
   uint32_t n_species;       /* 1 for the single-species entry points */
   uint64_t outlet_stride;   /* outlet sampled at steps 0, k, 2k, ...; 1 = every step (reference); 0 = none */
   uint64_t snapshot_stride; /* full profile at steps 0, k, 2k, ...; 1 = the whole trajectory; 0 = none */
+  /* Optional explicit sample lists (host pointers, read during the call only): strictly increasing step indices in
+   * [0, time_steps] — what sample_indices(time_steps + 1, n) returns (physics/traits.rs:1010-1023).  A non-NULL list
+   * replaces the corresponding stride: the outlet / snapshot buffers then hold exactly n_*_steps samples per column. */
+  const uint64_t* outlet_steps;
+  uint64_t n_outlet_steps;
+  const uint64_t* snapshot_steps;
+  uint64_t n_snapshot_steps;
 } chrom_run_cfg;
+
+/* Values per (column, species) of the on-device chromatogram summary, over ALL time steps at the detector cell:
+ *   [0] trapezoid area  sum 0.5 (c_k + c_k+1)(t_k+1 - t_k)           validation/dissimilarity.rs:81-88
+ *   [1] first moment    trapezoid(t c) / area   (retention time)     validation/main.rs:190-194
+ *   [2] maximum         [3] time of the maximum (first occurrence)
+ *   [4] sigma           sqrt(trapezoid((t - [1])^2 c) / area)        validation/main.rs:197-206
+ *   [5] minimum         (undershoot / oscillation indicator of the stability scans) */
+#define CHROM_SUMMARY_LEN 6
 
 typedef struct {
   double h2d_ms;    /* host->device copies (CUDA events, max over devices) */
@@ -133,6 +154,15 @@ int32_t chrom_cuda_bind_host_thread(chrom_cuda_ctx* ctx, int32_t device_index, i
 const char* chrom_cuda_validate_cfg(const chrom_run_cfg* cfg);
 /* Number of samples a stride produces: 0 if stride == 0 else time_steps / stride + 1. */
 uint64_t chrom_cuda_n_samples(uint64_t time_steps, uint64_t stride);
+/* Samples per column of the outlet / snapshot buffers for this configuration (list length, else the stride rule). */
+uint64_t chrom_cuda_cfg_n_out(const chrom_run_cfg* cfg);
+uint64_t chrom_cuda_cfg_n_snap(const chrom_run_cfg* cfg);
+/* sample_indices(total, Some(n)) of the reference (n == 0 or n >= total: every index; n == 1: [0]; else
+ * (i * (total - 1)) / (n - 1) with the last forced to total - 1).  Writes at most `cap` entries to out (may be NULL)
+ * and returns the number of indices the rule produces. */
+uint64_t chrom_cuda_sample_indices(uint64_t total, uint64_t n, uint64_t* out, uint64_t cap);
+/* Detector::node_index: round(position / (column_length / n_points)) clamped to n_points - 1 (position in metres). */
+uint32_t chrom_cuda_node_index(double position, double column_length, uint32_t n_points);
 /* out[0] = 0.0, out[s + 1] = ((double)s + 1.0) * dt  — (time_steps + 1) values. */
 void chrom_cuda_time_points(double total_time, uint64_t time_steps, double* out);
 /* Stages per step of a table: 3 for RK4 (t, t + dt/2.0, t + dt), 1 for Euler (t); t = (double)step * dt. */
@@ -154,8 +184,8 @@ size_t chrom_cuda_status_message(int64_t status, char* buf, size_t buf_len);
  * outlet     : [n_cols][n_out]        last cell at the sampled steps, or NULL
  * snapshots  : [n_cols][n_snap][nz]   full profiles at the sampled steps, or NULL
  * final_state: [n_cols][nz]           or NULL
- * summary    : [n_cols][4]            trapezoid area, first moment (time), max, time of max of the
- *                                     outlet over all steps, or NULL
+ * summary    : [n_cols][CHROM_SUMMARY_LEN]  area, first moment, max, time of max, sigma, min of the detector
+ *                                     signal over all steps (see CHROM_SUMMARY_LEN), or NULL
  * status     : [n_cols]               0 ok; +s = NaN first present after step s; -s = Inf (no NaN)
  *                                     after step s (validate_state runs after every step), or NULL */
 int32_t chrom_cuda_solve_single_batch(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, const chrom_single_col* cols,
@@ -165,7 +195,7 @@ int32_t chrom_cuda_solve_single_batch(chrom_cuda_ctx* ctx, const chrom_run_cfg* 
 
 /* State layout [n_cols][n_species][nz] (= nalgebra's column-major nz x n matrix per column).
  * outlet [n_cols][n_species][n_out]; snapshots [n_cols][n_snap][n_species][nz];
- * final_state [n_cols][n_species][nz]; summary [n_cols][n_species][4]; status [n_cols]. */
+ * final_state [n_cols][n_species][nz]; summary [n_cols][n_species][CHROM_SUMMARY_LEN]; status [n_cols]. */
 int32_t chrom_cuda_solve_multi_batch(chrom_cuda_ctx* ctx, const chrom_run_cfg* cfg, const chrom_multi_col* cols,
                                      uint64_t n_cols, const chrom_species* species, uint64_t n_species_total,
                                      const double* inj_tables, uint32_t n_tables, const double* y0,
@@ -191,6 +221,11 @@ int32_t chrom_cuda_plan_execute(chrom_cuda_plan* plan);
 /* Copies the requested outputs to host buffers (any may be NULL). */
 int32_t chrom_cuda_plan_download(chrom_cuda_plan* plan, double* outlet, double* snapshots, double* final_state,
                                  double* summary, int64_t* status);
+/* Surface resolution Rsf = integral |Y_a - Y_b| dt (Y = c / area) between the outlet series two executed plans hold
+ * on the device, per (column, species): the reference's Euler-vs-RK4 criterion (validation/main.rs:430-440) without
+ * moving either series to the host.  Both plans must have the same columns, species and outlet sampling (one time
+ * grid: rsf() then resamples nothing).  rsf: host [n_cols][n_species].  A series of zero area gives NaN. */
+int32_t chrom_cuda_plan_rsf(chrom_cuda_plan* a, chrom_cuda_plan* b, double* rsf);
 /* Human-readable description of the kernel variant and launch geometry chosen. */
 int32_t chrom_cuda_plan_describe(const chrom_cuda_plan* plan, char* buf, size_t buf_len);
 void chrom_cuda_plan_destroy(chrom_cuda_plan* plan);

@@ -56,7 +56,7 @@ def test_constants_match_header():
 
 def test_struct_layouts_match_header():
     assert C.sizeof(_ffi.SingleCol) == 56 and C.sizeof(_ffi.MultiCol) == 40 and C.sizeof(_ffi.Species) == 24
-    assert C.sizeof(_ffi.RunCfg) == 48 and C.sizeof(_ffi.Timing) == 56
+    assert C.sizeof(_ffi.RunCfg) == 80 and C.sizeof(_ffi.Timing) == 56  # 48 + two (pointer, count) sample lists
 
 
 def test_no_cpu_fallback():
@@ -242,3 +242,28 @@ def test_splitmix64_reference_stream():
     p = W.tfa_sweep_arrays(1000)
     assert 0.1 <= p["langmuir_k"].min() and p["langmuir_k"].max() <= 0.8 and 1.0 <= p["port_number"].min()
     assert p["port_number"].max() <= 3.0 and p["fe"].min() >= 1.0 - 1e-12 and p["fe"].max() <= 0.7 / 0.3 + 1e-12
+
+
+def test_sample_indices_and_node_index_known_answers():
+    """chrom_cuda_sample_indices / chrom_cuda_node_index against the reference's own doc and unit tests
+    (physics/traits.rs:1003-1023, 1466-1482; domain/detector.rs:278-290, 391-406)."""
+    import json
+    ka = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_known_answers.json")))
+    for c in ka["sample_indices"]["cases"]:
+        assert cb.sample_indices(c["total"], c["n"]).tolist() == c["expected"], c
+    for c in ka["detector_node_index"]["cases"]:
+        assert cb.node_index(c["position"], c["column_length"], c["n_points"]) == c["expected"], c
+    # the rule itself: n evenly spaced by integer division, last forced to total - 1, for a sweep of sizes
+    for total in (2, 7, 100, 10001):
+        for n in (2, 3, 5, 50, total - 1):
+            if n < 2 or n >= total:
+                continue
+            want = [(i * (total - 1)) // (n - 1) for i in range(n)]
+            want[-1] = total - 1
+            assert cb.sample_indices(total, n).tolist() == want
+    # a sample list turns into the buffer length the ABI expects
+    cfg = cb.make_cfg(cb.RK4, 600.0, 10000, 100, outlet_steps=cb.sample_indices(10001, 250), snapshot_stride=2500)
+    lib = _ffi.lib()
+    assert lib.chrom_cuda_cfg_n_out(C.byref(cfg)) == 250 and lib.chrom_cuda_cfg_n_snap(C.byref(cfg)) == 5
+    plain = cb.make_cfg(cb.RK4, 600.0, 10000, 100, outlet_stride=50)
+    assert lib.chrom_cuda_cfg_n_out(C.byref(plain)) == 201 and lib.chrom_cuda_cfg_n_snap(C.byref(plain)) == 0

@@ -287,3 +287,21 @@ def test_oracle_regression_vectors():
     from golden.make_oracle_vectors import cases
     for name, arr in cases().items():
         assert np.array_equal(arr.view(np.uint64), g[name].view(np.uint64)), name
+
+
+def test_mock_ode_values():
+    """rk4.rs:589-717 / euler.rs:475-548: the integrators on the reference's mock models (dy/dt = a y + b)."""
+    k = KA["mock_ode_values"]
+    g = k["constant_growth"]
+    for method in (O.RK4, O.EULER):
+        _, f, st = O.solve_linear_ode(method, 0.0, g["rate"], g["total_time"], g["steps"], [0.0])
+        assert st == 0 and abs(f[0] - g["expected_final"]) < g["abs_tol"]
+    for key, method in (("exponential_decay_rk4", O.RK4), ("exponential_decay_euler", O.EULER)):
+        d = k[key]
+        _, f, st = O.solve_linear_ode(method, d["rate"], 0.0, d["total_time"], d["steps"], [1.0])
+        assert st == 0 and abs(f[0] - np.exp(d["rate"] * d["total_time"])) < d["abs_tol"]
+    c = k["rk4_convergence"]
+    errs = [abs(O.solve_linear_ode(O.RK4, -0.1, 0.0, c["total_time"], s, [1.0])[1][0] - np.exp(-0.1 * c["total_time"]))
+            for s in c["steps"]]
+    for a, b in zip(errs, errs[1:]):
+        assert c["ratio_min"] < a / b < c["ratio_max"]
