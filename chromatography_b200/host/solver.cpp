@@ -31,34 +31,10 @@ SolverType SolverType::TimeEvolution(double total_time, std::size_t time_steps) 
   t.time_steps = time_steps;
   return t;
 }
-SolverType SolverType::Iterative(double tolerance, std::size_t max_iterations) {
+SolverType SolverType::Other(std::string name) {
   SolverType t;
-  t.kind_ = kIterative;
-  t.name_ = "Iterative";
-  t.tolerance = tolerance;
-  t.max_iterations = max_iterations;
-  return t;
-}
-SolverType SolverType::Analytical(std::optional<double> evaluation_time) {
-  SolverType t;
-  t.kind_ = kAnalytical;
-  t.name_ = "Analytical";
-  t.evaluation_time = evaluation_time;
-  return t;
-}
-SolverType SolverType::SpatialDiscretization(std::size_t grid_points, std::optional<std::size_t> time_steps) {
-  SolverType t;
-  t.kind_ = kSpatialDiscretization;
-  t.name_ = "SpatialDiscretization";
-  t.grid_points = grid_points;
-  t.sd_time_steps = time_steps;
-  return t;
-}
-SolverType SolverType::Custom(std::string name, std::map<std::string, double> parameters) {
-  SolverType t;
-  t.kind_ = kCustom;
+  t.kind_ = kOther;
   t.name_ = std::move(name);
-  t.parameters = std::move(parameters);
   return t;
 }
 
@@ -68,40 +44,17 @@ Result<Unit> SolverType::validate() const {
       if (total_time <= 0.0) return Err("Total time must be positive");
       if (time_steps == 0) return Err("TimeSteps must be greater than 0");
       return Ok();
-    case kIterative:
-      if (tolerance <= 0.0) return Err("Tolerance must be positive");
-      if (max_iterations == 0) return Err("Maximum iterations must be positive");
-      return Ok();
-    case kAnalytical: return Ok();
-    case kSpatialDiscretization:
-      if (grid_points == 0) return Err("Grid Points cannot be null (no grid)");
-      if (sd_time_steps && *sd_time_steps == 0) return Err("Steps must be greater than 0");
-      return Ok();
-    default:
-      for (const auto& kv : parameters)
-        if (!std::isfinite(kv.second)) return Err("Parameter " + kv.first + " is not finite");
-      return Ok();
+    default: return Ok();
   }
 }
 
 bool SolverType::operator==(const SolverType& o) const {
-  return kind_ == o.kind_ && name_ == o.name_ && total_time == o.total_time && time_steps == o.time_steps &&
-         tolerance == o.tolerance && max_iterations == o.max_iterations && evaluation_time == o.evaluation_time &&
-         grid_points == o.grid_points && sd_time_steps == o.sd_time_steps && parameters == o.parameters;
+  return kind_ == o.kind_ && name_ == o.name_ && total_time == o.total_time && time_steps == o.time_steps;
 }
 
 // ---- SolverConfiguration -------------------------------------------------------------------------------------
 SolverConfiguration SolverConfiguration::time_evolution(double total_time, std::size_t time_steps) {
   return SolverConfiguration(SolverType::TimeEvolution(total_time, time_steps));
-}
-SolverConfiguration SolverConfiguration::iterative(double tolerance, std::size_t max_iterations) {
-  return SolverConfiguration(SolverType::Iterative(tolerance, max_iterations));
-}
-SolverConfiguration SolverConfiguration::analytical(double evaluation_time) {
-  return SolverConfiguration(SolverType::Analytical(evaluation_time));
-}
-SolverConfiguration SolverConfiguration::spatial_discretization(std::size_t grid_points, std::size_t time_steps) {
-  return SolverConfiguration(SolverType::SpatialDiscretization(grid_points, time_steps));
 }
 SolverConfiguration SolverConfiguration::with_step(std::size_t n) const {
   SolverConfiguration c = *this;
@@ -137,36 +90,6 @@ DomainBoundaries DomainBoundaries::temporal(PhysicalState initial) {
   std::vector<DimensionBoundary> dims;
   dims.emplace_back("t", std::move(states));
   return DomainBoundaries(std::move(dims));
-}
-
-namespace {
-std::vector<DimensionBoundary> paired(const std::vector<std::string>& names, std::vector<PhysicalState>& begins,
-                                      std::vector<PhysicalState>& ends) {
-  if (names.size() != begins.size() || names.size() != ends.size())
-    throw std::invalid_argument("assertion `left == right` failed: names, begins and ends must have one entry per dimension");
-  std::vector<DimensionBoundary> dims;
-  for (std::size_t i = 0; i < names.size(); ++i) {
-    std::vector<PhysicalState> st;
-    st.push_back(std::move(begins[i]));
-    st.push_back(std::move(ends[i]));
-    dims.emplace_back(names[i], std::move(st));
-  }
-  return dims;
-}
-}  // namespace
-
-DomainBoundaries DomainBoundaries::spatial(const std::vector<std::string>& names, std::vector<PhysicalState> begins,
-                                           std::vector<PhysicalState> ends) {
-  return create(paired(names, begins, ends), TimeAxisConvention::none());
-}
-
-DomainBoundaries DomainBoundaries::mixed(const std::vector<std::string>& names, std::vector<PhysicalState> begins,
-                                         std::vector<PhysicalState> ends, PhysicalState initial) {
-  auto dims = paired(names, begins, ends);
-  std::vector<PhysicalState> st;
-  st.push_back(std::move(initial));
-  dims.emplace_back("t", std::move(st));
-  return create(std::move(dims), TimeAxisConvention::last());
 }
 
 std::size_t DomainBoundaries::sdim() const {

@@ -33,12 +33,13 @@ namespace chrom {
 // ---- SolverType ----------------------------------------------------------------------------------------
 class SolverType {
  public:
-  enum Kind { kTimeEvolution, kIterative, kAnalytical, kSpatialDiscretization, kCustom };
+  // The hot path is the time integrators: TimeEvolution is the one configuration RK4Solver / EulerSolver accept
+  // (rk4.rs:222-231, euler.rs:183-192).  The reference's other variants (Iterative, Analytical,
+  // SpatialDiscretization, Custom: traits.rs:172-215) belong to solvers outside this path; `Other(name)` stands for
+  // any of them so that the rejection ("... only supports TimeEvolution configuration, got <name>") stays testable.
+  enum Kind { kTimeEvolution, kOther };
   static SolverType TimeEvolution(double total_time, std::size_t time_steps);
-  static SolverType Iterative(double tolerance, std::size_t max_iterations);
-  static SolverType Analytical(std::optional<double> evaluation_time);
-  static SolverType SpatialDiscretization(std::size_t grid_points, std::optional<std::size_t> time_steps);
-  static SolverType Custom(std::string name, std::map<std::string, double> parameters);
+  static SolverType Other(std::string name);
 
   Kind kind() const { return kind_; }
   const std::string& name() const { return name_; }
@@ -46,12 +47,6 @@ class SolverType {
 
   double total_time = 0.0;                 // TimeEvolution
   std::size_t time_steps = 0;              // TimeEvolution
-  double tolerance = 0.0;                  // Iterative
-  std::size_t max_iterations = 0;          // Iterative
-  std::optional<double> evaluation_time;   // Analytical
-  std::size_t grid_points = 0;             // SpatialDiscretization
-  std::optional<std::size_t> sd_time_steps;  // SpatialDiscretization
-  std::map<std::string, double> parameters;  // Custom
   bool operator==(const SolverType& o) const;
 
  private:
@@ -67,9 +62,6 @@ struct SolverConfiguration {
   explicit SolverConfiguration(SolverType t) : solver_type(std::move(t)) {}
   static SolverConfiguration create(SolverType t) { return SolverConfiguration(std::move(t)); }  // `new`
   static SolverConfiguration time_evolution(double total_time, std::size_t time_steps);
-  static SolverConfiguration iterative(double tolerance, std::size_t max_iterations);
-  static SolverConfiguration analytical(double evaluation_time);
-  static SolverConfiguration spatial_discretization(std::size_t grid_points, std::size_t time_steps);
   SolverConfiguration with_step(std::size_t n) const;
   Result<Unit> validate() const { return solver_type.validate(); }
 };
@@ -108,10 +100,6 @@ struct DomainBoundaries {
       : dimensions(std::move(dims)), convention(TimeAxisConvention::last()) {}
   static DomainBoundaries create(std::vector<DimensionBoundary> dims, std::optional<TimeAxisConvention> convention);
   static DomainBoundaries temporal(PhysicalState initial);
-  static DomainBoundaries spatial(const std::vector<std::string>& names, std::vector<PhysicalState> begins,
-                                  std::vector<PhysicalState> ends);
-  static DomainBoundaries mixed(const std::vector<std::string>& names, std::vector<PhysicalState> begins,
-                                std::vector<PhysicalState> ends, PhysicalState initial);
 
   std::size_t ndim() const { return dimensions.size(); }
   std::size_t sdim() const;
