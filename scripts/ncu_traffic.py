@@ -40,7 +40,8 @@ def main():
         scale = float(scale) if scale else 1.0
         ks = read(rep)
         kname, rd, wr, dur, dur_u = ks[-1]
-        fam = ("single_stream" if "single_stream" in kname else "multi_reg" if "multi_reg" in kname else
+        fam = ("single_stream" if "single_stream" in kname else "multi_reg3" if "multi_reg3" in kname else "multi_reg2" if "multi_reg2" in kname else
+               "multi_reg" if "multi_reg" in kname else
                "multi_tiled" if "multi_tiled" in kname else "multi_resident" if "multi" in kname else
                "single_resident_mw" if "mw" in kname else "single_resident")
         table[name] = {"kernel_family": fam, "kernel": kname, "dram_bytes_read": rd * scale, "dram_bytes_write": wr * scale,
