@@ -276,14 +276,26 @@ class Ranks:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             if self.cuda:
                 dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+                # a second, CPU-only group: a rank waiting in an NCCL barrier keeps a spinning kernel on ITS GPU, which
+                # halves the rate of anything another process runs there (the one-context arm drives every GPU
+                # from rank 0: measured 188 ms instead of 87 ms at N = 2 before this)
+                self.host_group = dist.new_group(backend="gloo")
             else:
                 dist.init_process_group(backend)
+                self.host_group = None
 
     def barrier(self):
         if self.distributed:
             self.dist.barrier()
         if self.cuda:
             self.torch.cuda.synchronize()
+
+    def host_barrier(self):
+        """Wait for every rank on the host only: no kernel is queued on any GPU."""
+        if self.distributed:
+            if self.cuda:
+                self.torch.cuda.synchronize()
+            self.dist.barrier(group=self.host_group)
 
     def _reduce(self, x: float, op) -> float:
         if not self.distributed:
@@ -383,7 +395,7 @@ def host_d2h_ceiling(ranks, local_rank: int, nbytes: int, reps: int = 3) -> dict
 
 
 def run_workload(ctx, lib, ranks, args, spec, rank, world, local_rank, steps_k, warmup_w, arith_name="fast",
-                 scaling="strong", peak_tflops=0.0, main=False, want_cpu=True, numa=(-1, 0)):
+                 scaling="strong", peak_tflops=0.0, main=False, want_cpu=True, numa=(-1, 0), do_e2e=True):
     """One workload on this rank's share of the columns: value (plan-resident kernels), e2e (C-ABI call with host
     buffers), roofline, CPU baseline.  Returns (record for rank 0 or None, launches)."""
     import chromatography_b200 as cb
@@ -430,7 +442,7 @@ def run_workload(ctx, lib, ranks, args, spec, rank, world, local_rank, steps_k, 
 
     # ---- e2e: host buffers through the C-ABI solve call ----------------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if do_e2e and not args.no_e2e:
         sp = (spec["n_species"],) if spec["kind"] == "multi" else ()
         tables = inp["tables"]
         dp = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
@@ -548,12 +560,13 @@ def run_workload(ctx, lib, ranks, args, spec, rank, world, local_rank, steps_k, 
 
 
 def one_context_e2e(lib, ranks, spec, world, rank) -> dict | None:
-    """Rank 0 only: the SAME 65 536-column batch through ONE libchrom_cuda context spanning all N devices — one
-    caller buffer, the library shards it (chrom_cuda_shard_range) and copies every shard into its slice.  The other
-    ranks wait at the barrier with idle GPUs."""
+    """The library's own sharding: ONE chrom_cuda context over all `world` devices, driven by rank 0 alone through one
+    call with one set of caller buffers; the other ranks wait on the host (no kernel of
+    theirs sits on a GPU meanwhile).  Sweep mode (summary + strided outlet) and the full-rate outlet series."""
     import chromatography_b200 as cb
     slen = getattr(cb, "SUMMARY_LEN", 4)
     out = None
+    ranks.host_barrier()
     if rank == 0:
         ctx = cb.Context(list(range(world)))
         inp = build_inputs(spec, 0, 1, "strong")
@@ -561,32 +574,40 @@ def one_context_e2e(lib, ranks, spec, world, rank) -> dict | None:
         dp = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
         final, p1 = pinned_array(lib, (n_cols, spec["nz"]))
         status, p2 = pinned_array(lib, (n_cols,), np.int64)
-        summ, p3 = pinned_array(lib, (n_cols, slen))
-        n_out_s = spec["steps"] // SWEEP_OUTLET_STRIDE + 1
-        outlet_s, p4 = pinned_array(lib, (n_cols, n_out_s))
-        cfg_s = cb.make_cfg(cb.RK4, inp["total_time"], spec["steps"], spec["nz"], 1, SWEEP_OUTLET_STRIDE, 0, cb.ARITH_FAST)
         tables = inp["tables"]
 
-        def call():
-            ctx.check(lib.chrom_cuda_solve_single_batch(ctx._h, C.byref(cfg_s), inp["cols"], n_cols, dp(tables),
-                                                        tables.shape[0], None, dp(outlet_s), None, dp(final), dp(summ),
-                                                        status.ctypes.data_as(C.POINTER(C.c_int64))))
-            return ctx.timing()
+        def timed(stride, outlet, summ, reps=3):
+            cfg = cb.make_cfg(cb.RK4, inp["total_time"], spec["steps"], spec["nz"], 1, stride, 0, cb.ARITH_FAST)
 
-        call()
-        t0 = time.perf_counter()
-        reps = 3
-        for _ in range(reps):
-            tm = call()
-        ms = (time.perf_counter() - t0) * 1e3 / reps
-        out = {"value": units_of(spec, n_cols) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": reps,
-               "mode": "sweep", "devices": world, "h2d_bytes_per_step": int(tm["h2d_bytes"]),
-               "d2h_bytes_per_step": int(tm["d2h_bytes"]), "kernel_ms_max_over_devices": tm["kernel_ms"],
-               "api": "ONE chrom_cuda context over %d devices, one caller buffer (chrom_cuda_shard_range inside)" % world}
-        for p in (p1, p2, p3, p4):
+            def call():
+                ctx.check(lib.chrom_cuda_solve_single_batch(ctx._h, C.byref(cfg), inp["cols"], n_cols, dp(tables),
+                                                            tables.shape[0], None, dp(outlet), None, dp(final), dp(summ),
+                                                            status.ctypes.data_as(C.POINTER(C.c_int64))))
+                return ctx.timing()
+
+            call()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                tm = call()
+            ms = (time.perf_counter() - t0) * 1e3 / reps
+            return {"value": units_of(spec, n_cols) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": reps,
+                    "h2d_bytes_per_step": int(tm["h2d_bytes"]), "d2h_bytes_per_step": int(tm["d2h_bytes"]),
+                    "kernel_ms_max_over_devices": tm["kernel_ms"]}
+
+        summ, p3 = pinned_array(lib, (n_cols, slen))
+        outlet_s, p4 = pinned_array(lib, (n_cols, spec["steps"] // SWEEP_OUTLET_STRIDE + 1))
+        out = timed(SWEEP_OUTLET_STRIDE, outlet_s, summ)
+        out.update({"mode": "sweep", "devices": world,
+                    "api": "ONE chrom_cuda context over %d devices, one caller buffer (chrom_cuda_shard_range inside), "
+                           "driven by rank 0; the other ranks wait on the host" % world})
+        lib.chrom_cuda_host_free(p4)
+        lib.chrom_cuda_host_free(p3)
+        outlet, p5 = pinned_array(lib, (n_cols, spec["steps"] + 1))
+        out["full_outlet"] = timed(1, outlet, None)
+        for p in (p1, p2, p5):
             lib.chrom_cuda_host_free(p)
         ctx.close()
-    ranks.barrier()
+    ranks.host_barrier()
     return out
 
 
@@ -658,6 +679,16 @@ def main():
             launches += nl
             if r is not None:
                 extras[name] = r
+    weak = None
+    if world > 1 and default_run and args.scaling == "strong":
+        # the weak-scaling figure of round 1 (every rank its own full batch, kernels only) beside the strong-scaling line
+        r, nl = run_workload(ctx, lib, ranks, args, spec, rank, world, local_rank, max(1, min(3, args.steps)), 3, args.arith,
+                             "weak", peak_tflops, main=False, want_cpu=False, numa=numa, do_e2e=False)
+        launches += nl
+        if r is not None:
+            weak = {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "steps": r["steps"],
+                    "columns_total": r["config"]["columns_total"], "columns_per_rank": r["config"]["columns_rank0"],
+                    "note": "weak scaling: independent processes, every rank its own full batch, kernels only (no e2e)"}
     one_ctx = None
     if world > 1 and args.workload == "c3" and not args.no_e2e and not args.cols:
         ctx.close()
@@ -678,6 +709,8 @@ def main():
                      "reference's operation order)",
             "l2": f"256 MiB buffer written between timed iterations (L2 flush); full-rate outlet series {out_gb:.2f} GB per batch",
             "e2e_mode": (e2e or {}).get("mode")})
+        if weak is not None:
+            cfg["weak"] = weak
         line = {
             "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W_,
             "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
