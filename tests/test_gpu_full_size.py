@@ -5,6 +5,8 @@ The oracle cannot run 65 536 x 10 000 steps in seconds, so the full-size runs ar
   * a size-independent property of the domain: columns are independent scenarios, so a column's result must
     not depend on where in the batch (which warp / CTA / wave) it was solved — the same columns re-solved as
     a small batch must agree with the full-size run bit for bit,
+  * EVERY column, not a sample: the full batch is solved a second time in EXACT arithmetic (bit-identical to the oracle
+    on the sampled columns, checked here) and the FAST run must agree with it within 1e-9 on every entry of every column,
   * validate_state: every status 0, every summary finite, mass recovered at the outlet within physical bounds.
 Config 4 at full size: tests/test_gpu_stream.py::test_full_size_prefix_property.
 """
@@ -44,6 +46,16 @@ def test_c3_full_size(ctx):
         assert abs(r.summary[i][0] - area) <= MOMENT_RTOL * max(area, 1e-300), i
         if area > 1e-12:
             assert abs(r.summary[i][1] - tr) <= MOMENT_RTOL * tr, i
+    # every column: the EXACT run of the whole batch carries the oracle's bits on the sample, and FAST agrees with it
+    # within the contract on all 65 536 columns
+    cfg_x = cb.make_cfg(cb.RK4, T, steps, nz, 1, stride, 0, cb.ARITH_EXACT)
+    x = cb.solve_single_batch(ctx, cfg_x, cols, tables, None, True, False, True, False)
+    assert not x.status.any()
+    for k, i in enumerate(sample):
+        assert_bit_equal(x.outlet[i], oo[k][::stride], f"EXACT outlet of column {i} vs oracle")
+        assert_bit_equal(x.final_state[i], of[k], f"EXACT final state of column {i} vs oracle")
+    assert max_rel_err(r.outlet, x.outlet) <= PROFILE_RTOL
+    assert max_rel_err(r.final_state, x.final_state) <= PROFILE_RTOL
     # batch-position independence, bit for bit
     sub = (_ffi.SingleCol * len(sample))(*[cols[int(i)] for i in sample])
     s = cb.solve_single_batch(ctx, cfg, sub, tables, None, True, False, True, True)
@@ -67,6 +79,15 @@ def test_c5_full_size(ctx):
     for k, i in enumerate(sample):
         assert max_rel_err(r.outlet[i], oo[k][:, ::stride]) <= PROFILE_RTOL, i
         assert max_rel_err(r.final_state[i], of[k]) <= PROFILE_RTOL, i
+    # every column: EXACT (nalgebra LU order; the oracle's bits on the sample) against FAST on all 4 096 columns
+    cfg_x = cb.make_cfg(cb.RK4, T, steps, nz, n, stride, 0, cb.ARITH_EXACT)
+    x = cb.solve_multi_batch(ctx, cfg_x, cols, species, tables, None, True, False, True, False)
+    assert not x.status.any()
+    for k, i in enumerate(sample):
+        assert_bit_equal(x.outlet[i], oo[k][:, ::stride], f"EXACT outlet of column {i} vs oracle")
+        assert_bit_equal(x.final_state[i], of[k], f"EXACT final state of column {i} vs oracle")
+    assert max_rel_err(r.outlet, x.outlet) <= PROFILE_RTOL
+    assert max_rel_err(r.final_state, x.final_state) <= PROFILE_RTOL
     # batch-position independence, bit for bit: 20 columns re-solved on their own
     rng = np.random.default_rng(5)
     pick = np.sort(rng.choice(n_cols, size=20, replace=False))
