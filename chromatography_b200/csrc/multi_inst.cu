@@ -2,6 +2,7 @@
 // so that the nine instantiation sets of multi_kernels.cuh / multi_tiled.cuh build in parallel.
 #include "multi_reg.cuh"
 #include "multi_reg2.cuh"
+#include "multi_reg3.cuh"
 #include "multi_tiled.cuh"
 
 #define CHROM_CAT2(a, b) a##b
@@ -26,6 +27,8 @@ int CHROM_CAT(multi_reg_tmax_, CHROM_MULTI_N)(int m) {  // threads per CTA; nega
 #if CHROM_MULTI_N > 0 && CHROM_MULTI_N <= 8  // second-generation register-resident kernels: n = 1..8
 rkern_t CHROM_CAT(multi_reg2_pick_, CHROM_MULTI_N)(int method) { return pick_reg2_n<CHROM_MULTI_N>(method); }
 int CHROM_CAT(multi_reg2_tmax_, CHROM_MULTI_N)() { return reg2_tmax_rt<CHROM_MULTI_N>(); }
+// third generation (multi_reg3.cuh): same geometry, the pivoting guard per column run; sync = the seam protocol
+rkern_t CHROM_CAT(multi_reg3_pick_, CHROM_MULTI_N)(int method, int sync) { return pick_reg3_n<CHROM_MULTI_N>(method, sync); }
 #endif
 #if CHROM_MULTI_N == 0
 void multi_tiled_init_launch(const BatchDev& b, double* ping, unsigned long long* code, cudaStream_t s) {

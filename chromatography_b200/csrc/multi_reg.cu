@@ -14,8 +14,9 @@ typedef void (*rkern_t)(const BatchDev);
 CHROM_DECL(1) CHROM_DECL(2) CHROM_DECL(3) CHROM_DECL(4) CHROM_DECL(5) CHROM_DECL(6) CHROM_DECL(7) CHROM_DECL(8)
 CHROM_DECL(9) CHROM_DECL(10) CHROM_DECL(11) CHROM_DECL(12) CHROM_DECL(13) CHROM_DECL(14) CHROM_DECL(15) CHROM_DECL(16)
 #undef CHROM_DECL
-#define CHROM_DECL2(N)                      \
-  rkern_t multi_reg2_pick_##N(int method);  \
+#define CHROM_DECL2(N)                                \
+  rkern_t multi_reg2_pick_##N(int method);            \
+  rkern_t multi_reg3_pick_##N(int method, int sync);  \
   int multi_reg2_tmax_##N();
 CHROM_DECL2(1) CHROM_DECL2(2) CHROM_DECL2(3) CHROM_DECL2(4) CHROM_DECL2(5) CHROM_DECL2(6) CHROM_DECL2(7) CHROM_DECL2(8)
 #undef CHROM_DECL2
@@ -33,6 +34,21 @@ rkern_t lookup_reg2(int n, int method) {
     case 6: return multi_reg2_pick_6(method);
     case 7: return multi_reg2_pick_7(method);
     case 8: return multi_reg2_pick_8(method);
+  }
+  return nullptr;
+}
+
+// third-generation kernels (multi_reg3.cuh): the geometry of the second, guard per column run, seam protocol `sync`
+rkern_t lookup_reg3(int n, int method, int sync) {
+  switch (n) {
+    case 1: return multi_reg3_pick_1(method, sync);
+    case 2: return multi_reg3_pick_2(method, sync);
+    case 3: return multi_reg3_pick_3(method, sync);
+    case 4: return multi_reg3_pick_4(method, sync);
+    case 5: return multi_reg3_pick_5(method, sync);
+    case 6: return multi_reg3_pick_6(method, sync);
+    case 7: return multi_reg3_pick_7(method, sync);
+    case 8: return multi_reg3_pick_8(method, sync);
   }
   return nullptr;
 }
@@ -99,24 +115,40 @@ int tmax_reg(int n, int m) {
 
 constexpr int kReg2MinSpecies = 5;
 
-// Second-generation kernel: chosen when CHROM_REG2 names a variant (experiments) or by default where measured faster.
+// Generation of the 2-cells-per-thread kernels (n <= 8): 3 = multi_reg3.cuh (guard per column run), 2 = multi_reg2.cuh.
+// CHROM_REG2 = 2 / 3 forces one (experiments, A/B tests), CHROM_REG3_SYNC picks the seam protocol of the third.
+constexpr int kReg3DefaultSync = 0;
+static int reg_generation() {
+  const char* v = getenv("CHROM_REG2");
+  return v ? atoi(v) : 3;
+}
+static int reg3_sync() {
+  const char* v = getenv("CHROM_REG3_SYNC");
+  const int s = v ? atoi(v) : kReg3DefaultSync;
+  return (s < 0 || s > 2) ? kReg3DefaultSync : s;
+}
+
 static bool multi_reg2_choose(const BatchDev& b, int sm_count, LaunchGeom* g) {
   const int n = (int)b.n_species;
   if (n < 1 || n > 8) return false;
   const int M = 2;
+  const int gen = reg_generation() == 2 ? 2 : 3;
+  const int sync = reg3_sync();
   const int tmax = tmax_reg2(n);
   const int T = (int)(((b.nz + M - 1) / M + 31u) / 32u * 32u);
   if (tmax == 0 || T > tmax) return false;
-  rkern_t k = lookup_reg2(n, b.method);
+  rkern_t k = gen == 3 ? lookup_reg3(n, b.method, sync) : lookup_reg2(n, b.method);
   if (!k) return false;
-  // seam ring: 8 slots x warps x (n | 1); dense-fallback scratch: warps x (3 n + n n)
-  const size_t smem = ((size_t)8 * (T / 32) * (n | 1) + (size_t)(T / 32) * (3 * n + n * n)) * sizeof(double);
+  // seam ring: 8 slots x warps x row (n | 1 doubles, or n rounded up to even: n + 2 covers both); dense-fallback
+  // scratch: warps x (3 n + n n)
+  const size_t smem = ((size_t)8 * (T / 32) * (n + 2) + (size_t)(T / 32) * (3 * n + n * n)) * sizeof(double);
   int per_sm = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, T, smem) != cudaSuccess || per_sm < 1) {
     cudaGetLastError();
     per_sm = 1;
   }
   g->kind = 7;
+  g->wj = gen == 3 ? 1 + sync : 0;  // which kernel multi_reg2_launch starts
   g->M = M;
   g->L = T;
   g->cpw = 1;
@@ -127,15 +159,16 @@ static bool multi_reg2_choose(const BatchDev& b, int sm_count, LaunchGeom* g) {
   g->smem = smem;
   char buf[240];
   snprintf(buf, sizeof buf,
-           "multi_reg2<n=%d,%s,fast-scan-LU> threads/col=%d cells/thread=%d CTAs/SM=%d persistent grid=%u", n,
-           b.method == CHROM_RK4 ? "RK4" : "Euler", T, M,
+           "multi_reg%d<n=%d,%s,fast-scan-LU%s> threads/col=%d cells/thread=%d CTAs/SM=%d persistent grid=%u", gen, n,
+           b.method == CHROM_RK4 ? "RK4" : "Euler",
+           gen == 3 ? (sync == 0 ? ",seam=flags" : sync == 1 ? ",seam=mbarrier" : ",seam=mbarrier-nobar") : "", T, M,
            per_sm, g->grid.x);
   g->name = buf;
   return true;
 }
 
 cudaError_t multi_reg2_launch(const BatchDev& b, const LaunchGeom& g, cudaStream_t s) {
-  rkern_t k = lookup_reg2((int)b.n_species, b.method);
+  rkern_t k = g.wj >= 1 ? lookup_reg3((int)b.n_species, b.method, g.wj - 1) : lookup_reg2((int)b.n_species, b.method);
   if (!k) return cudaErrorInvalidValue;
   const uint32_t grid = std::min<uint32_t>(b.n_cols, g.cols_per_wave ? g.cols_per_wave : b.n_cols);
   k<<<dim3(grid), g.block, g.smem, s>>>(b);
@@ -149,13 +182,14 @@ bool multi_reg_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::strin
     if (why) *why = "register-resident multi kernel covers n_species 1..16";
     return false;
   }
-  // Second generation (multi_reg2.cuh) where it measured faster on B200 (profiles/r2_multi_shapes.jsonl): n >= 5
-  // (C5 645 -> 471 ms, n = 7 nz = 200 141 -> 103 ms, n = 6 nz = 256 107 -> 81 ms, n = 5 nz = 300 108 -> 94 ms); n <= 4
-  // stays with the first generation (2 or 4 cells per thread, shared-memory exchange: 1.84e11 vs 1.71e11 cell-stage/s
-  // at n = 2).  CHROM_REG2 = 0 forces the first generation, 2 the second (experiments).
+  // Two cells per thread with acc in registers and the shuffle/seam exchange (multi_reg2.cuh, multi_reg3.cuh) where
+  // it measured faster on B200 (profiles/r2_multi_shapes.jsonl): n >= 5 (C5 645 -> 471 ms, n = 7 nz = 200 141 -> 103
+  // ms, n = 6 nz = 256 107 -> 81 ms, n = 5 nz = 300 108 -> 94 ms); n <= 4 stays with the first generation (2 or 4
+  // cells per thread, shared-memory exchange: 1.84e11 vs 1.71e11 cell-stage/s at n = 2).  CHROM_REG2 = 0 forces the
+  // first generation, 2 / 3 the second / third for every n <= 8 (experiments).
   {
-    const char* v2 = getenv("CHROM_REG2");
-    const bool second = v2 ? atoi(v2) != 0 : n >= kReg2MinSpecies;
+    const int gen = reg_generation();
+    const bool second = getenv("CHROM_REG2") ? gen != 0 : n >= kReg2MinSpecies;
     if (second && multi_reg2_choose(b, sm_count, g)) return true;
   }
   const char* force = getenv("CHROM_REG_M");

@@ -108,6 +108,32 @@ def test_species_counts_exact_and_fast(ctx, n, nz):
         assert max_rel_err(f.outlet[0], ref.outlet) <= PROFILE_RTOL
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("nz", [33, 100, 512])
+def test_species_counts_euler(ctx, n, nz):
+    """EulerSolver (euler.rs:227-269) through every kernel family that serves n <= 8: EXACT bit-identical, FAST and
+    FAST_DENSE within 1e-9, three columns per batch (the persistent-CTA column loop), several warps per column."""
+    steps = 90
+    T = steps * 0.2 * (0.25 / 100.0) / (1e-3 / 0.4)
+    rng = np.random.default_rng(7 * n + nz)
+    y0 = rng.uniform(0.0, 0.05, size=(nz, n))
+    m = cb.LangmuirMulti.new(random_species(n, seed=n), nz, 0.4, 1e-3, 0.25 * nz / 100.0)
+    ref = O.solve_multi(to_oracle(m), O.EULER, T, steps, y0=y0, want_trajectory=True)
+    y0_dev = np.repeat(np.ascontiguousarray(y0.T)[None], 3, axis=0)
+    r = run_gpu(ctx, [m] * 3, cb.EULER, T, steps, cb.ARITH_EXACT, y0=y0_dev, snapshot_stride=30)
+    assert not r.status.any() and ref.status == 0
+    for c in range(3):
+        assert_bit_equal(r.snapshots[c].transpose(0, 2, 1), ref.trajectory[::30], f"n={n} nz={nz} snapshots")
+        assert_bit_equal(r.outlet[c], ref.outlet, f"n={n} nz={nz} outlet")
+    for arith in (cb.ARITH_FAST, cb.ARITH_FAST_DENSE):
+        f = run_gpu(ctx, [m] * 3, cb.EULER, T, steps, arith, y0=y0_dev, snapshot_stride=30, want_summary=True)
+        assert not f.status.any()
+        for c in range(3):
+            assert max_rel_err(f.snapshots[c].transpose(0, 2, 1), ref.trajectory[::30]) <= PROFILE_RTOL
+            assert max_rel_err(f.final_state[c].T, ref.final_state) <= PROFILE_RTOL
+            assert max_rel_err(f.outlet[c], ref.outlet) <= PROFILE_RTOL
+
+
 @pytest.mark.parametrize("n", [9, 12, 16, 24, 40])
 @pytest.mark.parametrize("method", [cb.RK4, cb.EULER], ids=["rk4", "euler"])
 def test_many_species_runtime_n(ctx, n, method):
