@@ -29,6 +29,9 @@
 //          for its downstream warp to have consumed the slot it is about to overwrite (two steps back), nothing
 //          else; warp 0 publishes the inlet row for itself; the redo flag is polled with a CTA barrier every 64
 //          steps only.
+//       3  protocol 1 with branch-free seam code: the store and the arrival are predicated on lane 31, and on the
+//          consumer side EVERY lane waits on the barrier and loads the row (a broadcast), lane 0 keeps it by select;
+//          a stage then has no divergent branch at all.
 //     The mbarriers are initialised ONCE per kernel.  (Re-initialising them per run with mbarrier.inval +
 //     mbarrier.init stalled on B200: C5 and an abandoned Euler run never finished, first GPU session of this
 //     kernel.)  Instead the phase bookkeeping runs on a CTA-wide step counter that continues across runs and
@@ -61,6 +64,39 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       : "memory");
 }
 
+// predicated forms (SYNC 3): the seam store and the arrival are issued by every lane under a predicate instead of
+// inside a divergent branch (no BSSY / BRA / BSYNC around five instructions)
+__device__ __forceinline__ void st_shared_v2_if(bool p, double* dst, double a, double b) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %0, 0;\n"
+      "@p st.shared.v2.f64 [%1], {%2, %3};\n"
+      "}\n" ::"r"((int)p),
+      "r"(smem_u32(dst)), "d"(a), "d"(b)
+      : "memory");
+}
+__device__ __forceinline__ void st_shared_if(bool p, double* dst, double a) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %0, 0;\n"
+      "@p st.shared.f64 [%1], %2;\n"
+      "}\n" ::"r"((int)p),
+      "r"(smem_u32(dst)), "d"(a)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_if(bool p, unsigned long long* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %0, 0;\n"
+      "@p mbarrier.arrive.shared::cta.b64 _, [%1];\n"
+      "}\n" ::"r"((int)p),
+      "r"(smem_u32(bar))
+      : "memory");
+}
+
 constexpr int kReg3CheckEvery = 64;  // SYNC 2: steps between two CTA-wide polls of the redo flag
 
 template <int N, int M, int METHOD, int SYNC>
@@ -69,7 +105,7 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
   constexpr int XS = (SYNC == 0) ? (N | 1) : ((N + 1) & ~1);  // seam rows: odd stride / 16-byte rows (STS.128)
   constexpr int kMaxW = 32;
   __shared__ SpeciesConst sc[N];
-  __shared__ double inlet[2][3][N];  // [step parity][stage row][species]
+  __shared__ __align__(16) double inlet[2][3][N];  // [step parity][stage row][species]
   __shared__ Summ summ[N];           // running summary of the detector signal (detector owner only)
   __shared__ const double* tabs[N];
   __shared__ double colc[2];              // 2 max_i K_i, min_i (1 + fe lambda_i) of the current column
@@ -202,6 +238,19 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
       // barrier, its arrival completes phase k of the full barrier, the consumer's completes phase k + 1 of the empty.
       auto post = [&](const double (&last)[N], int slot, uint32_t g) {
         if (SYNC == 0) ++posted;
+        if (SYNC == 3) {
+          const bool poster = (lane == 31) && (warp + 1 < W);
+          double* dst = seam + ((size_t)slot * W + warp) * XS;
+          if (N % 2 == 0) {
+#pragma unroll
+            for (int s = 0; s + 1 < N; s += 2) st_shared_v2_if(poster, dst + s, last[s], last[s + 1]);
+          } else {
+#pragma unroll
+            for (int s = 0; s < N; ++s) st_shared_if(poster, dst + s, last[s]);
+          }
+          mbar_arrive_if(poster, full_bar(slot, warp));
+          return;
+        }
         if (lane == 31 && warp + 1 < W) {
           double* dst = seam + ((size_t)slot * W + warp) * XS;
           if (SYNC == 2) mbar_wait(empty_bar(slot, warp), (g >> 1) & 1u);
@@ -273,7 +322,27 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
           cell(j, u[j - 1]);
           if (j == M - 1) post(u[M - 1], slot_next, g_next);
         }
-        if (lane == 0) {  // the first lane's upstream cell: the inlet (warp 0) or the upstream warp's last cell
+        if (SYNC == 3) {  // warp-uniform: every lane waits and loads the row (a broadcast), lane 0 keeps it
+          const double* srcp = &inlet[spar][irow][0];
+          if (warp != 0) {
+            mbar_wait(full_bar(slot, warp - 1), (g >> 1) & 1u);
+            srcp = seam + ((size_t)slot * W + (warp - 1)) * XS;
+          }
+          if (N % 2 == 0) {
+#pragma unroll
+            for (int s = 0; s + 1 < N; s += 2) {
+              const double2 t = reinterpret_cast<const double2*>(srcp)[s / 2];
+              up[s] = (lane == 0) ? t.x : up[s];
+              up[s + 1] = (lane == 0) ? t.y : up[s + 1];
+            }
+          } else {
+#pragma unroll
+            for (int s = 0; s < N; ++s) {
+              const double t = srcp[s];
+              up[s] = (lane == 0) ? t : up[s];
+            }
+          }
+        } else if (lane == 0) {  // the first lane's upstream cell: the inlet (warp 0) or the upstream warp's last cell
           if (warp == 0) {
 #pragma unroll
             for (int s = 0; s < N; ++s) up[s] = inlet[spar][irow][s];
@@ -437,6 +506,7 @@ rkern_t pick_reg3_n(int method, int sync) {
       case 0: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 0> : k_multi_reg3<N, 2, CHROM_EULER, 0>;
       case 1: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 1> : k_multi_reg3<N, 2, CHROM_EULER, 1>;
       case 2: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 2> : k_multi_reg3<N, 2, CHROM_EULER, 2>;
+      case 3: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 3> : k_multi_reg3<N, 2, CHROM_EULER, 3>;
     }
   }
   return nullptr;

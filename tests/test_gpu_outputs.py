@@ -82,11 +82,19 @@ def run_single(ctx, models, T, steps, arith=cb.ARITH_FAST, method=cb.RK4, want=W
 def multi_case(kind):
     if kind == "reg":      # first-generation register kernel (n <= 4)
         return [W.acids_multi()], 600.0, 3000, "multi_reg<"
-    if kind == "reg2":     # second generation (n >= 6)
+    if kind == "reg2":     # second generation (forced with CHROM_REG2 = 2 by the tests: see force_generation)
         return W.multi_batch_models(2, 6, 64, seed=5), 300.0, 500, "multi_reg2<"
+    if kind == "reg3":     # third generation: the default for n >= 5
+        return W.multi_batch_models(2, 6, 64, seed=5), 300.0, 500, "multi_reg3<"
     if kind == "resident":  # shared-memory resident (EXACT arithmetic)
         return W.multi_batch_models(2, 3, 96, seed=6), 300.0, 500, "multi_resident<"
     return W.multi_batch_models(1, 20, 40, seed=9), 100.0, 120, "multi_tiled<"  # warp per cell
+
+
+def force_generation(monkeypatch, kind):
+    """The register-resident kernel generation is chosen when the plan is built (csrc/multi_reg.cu)."""
+    if kind == "reg2":
+        monkeypatch.setenv("CHROM_REG2", "2")
 
 
 def run_multi(ctx, models, T, steps, arith=cb.ARITH_FAST, want=WANT_ALL, **cfg_kw):
@@ -120,8 +128,9 @@ def test_summary_single(ctx, kind):
         assert max_rel_err(r.outlet[c], series[::7]) <= PROFILE_RTOL
 
 
-@pytest.mark.parametrize("kind", ["reg", "reg2", "resident", "tiled"])
-def test_summary_multi(ctx, kind):
+@pytest.mark.parametrize("kind", ["reg", "reg2", "reg3", "resident", "tiled"])
+def test_summary_multi(ctx, kind, monkeypatch):
+    force_generation(monkeypatch, kind)
     models, T, steps, family = multi_case(kind)
     arith = cb.ARITH_EXACT if kind == "resident" else cb.ARITH_FAST
     r, desc = run_multi(ctx, models, T, steps, arith=arith)
@@ -168,12 +177,13 @@ def test_sample_lists_single(ctx, kind):
         assert_bit_equal(r.snapshots[c], ref.trajectory[snap_steps.astype(int)], f"{kind} snapshot list")
 
 
-@pytest.mark.parametrize("kind", ["reg", "reg2", "resident", "tiled"])
-def test_sample_lists_multi(ctx, kind):
+@pytest.mark.parametrize("kind", ["reg", "reg2", "reg3", "resident", "tiled"])
+def test_sample_lists_multi(ctx, kind, monkeypatch):
+    force_generation(monkeypatch, kind)
     models, T, steps, family = multi_case(kind)
     out_steps = cb.sample_indices(steps + 1, 23)
     snap_steps = np.array([0, 3, steps - 1], dtype=np.uint64)
-    arith = cb.ARITH_FAST if kind in ("reg", "reg2") else cb.ARITH_EXACT
+    arith = cb.ARITH_FAST if kind in ("reg", "reg2", "reg3") else cb.ARITH_EXACT
     r, desc = run_multi(ctx, models, T, steps, arith=arith, outlet_steps=out_steps, snapshot_steps=snap_steps)
     if arith == cb.ARITH_FAST:
         assert family in desc
@@ -224,14 +234,15 @@ def test_detector_cell_single(ctx, kind):
         check_summary(r.summary[c], tp, series, f"{kind} detector at cell {cell}")
 
 
-@pytest.mark.parametrize("kind", ["reg", "reg2", "resident", "tiled"])
-def test_detector_cell_multi(ctx, kind):
+@pytest.mark.parametrize("kind", ["reg", "reg2", "reg3", "resident", "tiled"])
+def test_detector_cell_multi(ctx, kind, monkeypatch):
+    force_generation(monkeypatch, kind)
     models, T, steps, family = multi_case(kind)
     nz = models[0].n_points
     cells = [nz // 2, 1][:len(models)]
     for m, cell in zip(models, cells):
         m.detector_cell = cell + 1
-    arith = cb.ARITH_FAST if kind in ("reg", "reg2") else cb.ARITH_EXACT
+    arith = cb.ARITH_FAST if kind in ("reg", "reg2", "reg3") else cb.ARITH_EXACT
     r, desc = run_multi(ctx, models, T, steps, arith=arith)
     tp = cb.time_points(T, steps)
     for c, (m, cell) in enumerate(zip(models, cells)):

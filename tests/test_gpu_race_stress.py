@@ -2,7 +2,7 @@
 
 The register- and shared-memory-resident kernels synchronise by hand: double-buffered inlet rows, one barrier per
 stage or per step, a seam ring between adjacent warps guarded by release/acquire counters
-(multi_reg2.cuh), warp-boundary cells through shared memory (single_resident.cu, multi-warp columns), ping-pong stage
+(multi_reg2.cuh, multi_reg3.cuh: counters or mbarriers), warp-boundary cells through shared memory (single_resident.cu, multi-warp columns), ping-pong stage
 buffers (multi_kernels.cuh), tile halos (multi_tiled.cuh, single_stream.cu).  A race in any of them shows up as
 timing-dependent bits.  So: a batch of IDENTICAL columns, several per persistent CTA and more CTAs than the machine
 holds at once, is solved repeatedly; every column of every run must carry exactly the bits of column 0 of run 0, and
@@ -40,9 +40,13 @@ def _multi_model(n, nz, seed):
 
 # (n_species, nz, arithmetic, environment): every hand-synchronised multi-species kernel family
 MULTI_CASES = [
-    (8, 512, cb.ARITH_FAST, {}),                       # k_multi_reg2: 8 warps, seam ring, one barrier per step
-    (6, 200, cb.ARITH_FAST, {}),                       # k_multi_reg2, ragged last warp
-    (5, 97, cb.ARITH_FAST, {}),                        # k_multi_reg2, odd n, nz not a multiple of anything
+    (8, 512, cb.ARITH_FAST, {}),                       # k_multi_reg3: 8 warps, seam ring, one barrier per step
+    (6, 200, cb.ARITH_FAST, {}),                       # k_multi_reg3, ragged last warp
+    (5, 97, cb.ARITH_FAST, {}),                        # k_multi_reg3, odd n, nz not a multiple of anything
+    (8, 512, cb.ARITH_FAST, {"CHROM_REG3_SYNC": "0"}),  # k_multi_reg3, release/acquire counters instead of mbarriers
+    (8, 512, cb.ARITH_FAST, {"CHROM_REG3_SYNC": "2"}),  # k_multi_reg3, full + empty mbarriers, no per-step CTA barrier
+    (7, 300, cb.ARITH_FAST, {"CHROM_REG3_SYNC": "3"}),  # k_multi_reg3, predicated seam code
+    (8, 512, cb.ARITH_FAST, {"CHROM_REG2": "2"}),      # k_multi_reg2 (second generation, guard per cell)
     (2, 300, cb.ARITH_FAST, {}),                       # k_multi_reg: shared-memory exchange, one barrier per stage
     (12, 256, cb.ARITH_FAST, {}),                      # k_multi_reg, acc in shared slots
     (8, 512, cb.ARITH_FAST_DENSE, {}),                 # k_multi_resident: ping-pong stage buffers
@@ -53,7 +57,8 @@ MULTI_CASES = [
 
 
 @pytest.mark.parametrize("n,nz,arith,env", MULTI_CASES,
-                         ids=[f"n{n}-nz{nz}-a{a}{'-tiled' if e else ''}" for n, nz, a, e in MULTI_CASES])
+                         ids=[f"n{n}-nz{nz}-a{a}" + "".join("-" + k.split("_")[-1].lower() + v for k, v in e.items() if len(v) < 3)
+                              for n, nz, a, e in MULTI_CASES])
 def test_identical_multi_columns_agree_bit_for_bit(ctx, monkeypatch, n, nz, arith, env):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
