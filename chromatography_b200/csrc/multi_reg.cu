@@ -117,7 +117,7 @@ constexpr int kReg2MinSpecies = 5;
 
 // Generation of the 2-cells-per-thread kernels (n <= 8): 3 = multi_reg3.cuh (guard per column run), 2 = multi_reg2.cuh.
 // CHROM_REG2 = 2 / 3 forces one (experiments, A/B tests), CHROM_REG3_SYNC picks the seam protocol of the third.
-constexpr int kReg3DefaultSync = 1;
+constexpr int kReg3DefaultSync = 3;
 static int reg_generation() {
   const char* v = getenv("CHROM_REG2");
   return v ? atoi(v) : 3;
