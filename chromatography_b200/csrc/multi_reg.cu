@@ -125,7 +125,7 @@ static int reg_generation() {
 static int reg3_sync() {
   const char* v = getenv("CHROM_REG3_SYNC");
   const int s = v ? atoi(v) : kReg3DefaultSync;
-  return (s < 0 || s > 3) ? kReg3DefaultSync : s;
+  return (s < 0 || s > 4) ? kReg3DefaultSync : s;
 }
 
 static bool multi_reg2_choose(const BatchDev& b, int sm_count, LaunchGeom* g) {
@@ -162,7 +162,8 @@ static bool multi_reg2_choose(const BatchDev& b, int sm_count, LaunchGeom* g) {
            "multi_reg%d<n=%d,%s,fast-scan-LU%s> threads/col=%d cells/thread=%d CTAs/SM=%d persistent grid=%u", gen, n,
            b.method == CHROM_RK4 ? "RK4" : "Euler",
            gen == 3 ? (sync == 0 ? ",seam=flags" : sync == 1 ? ",seam=mbarrier" : sync == 2 ? ",seam=mbarrier-nobar"
-                                                                                    : ",seam=mbarrier-flat")
+                                                                 : sync == 3 ? ",seam=mbarrier-flat"
+                                                                             : ",seam=mbarrier-flat-splitbar")
                     : "", T, M,
            per_sm, g->grid.x);
   g->name = buf;
@@ -184,14 +185,18 @@ bool multi_reg_choose(const BatchDev& b, int sm_count, LaunchGeom* g, std::strin
     if (why) *why = "register-resident multi kernel covers n_species 1..16";
     return false;
   }
-  // Two cells per thread with acc in registers and the shuffle/seam exchange (multi_reg2.cuh, multi_reg3.cuh) where
-  // it measured faster on B200 (profiles/r2_multi_shapes.jsonl): n >= 5 (C5 645 -> 471 ms, n = 7 nz = 200 141 -> 103
-  // ms, n = 6 nz = 256 107 -> 81 ms, n = 5 nz = 300 108 -> 94 ms); n <= 4 stays with the first generation (2 or 4
-  // cells per thread, shared-memory exchange: 1.84e11 vs 1.71e11 cell-stage/s at n = 2).  CHROM_REG2 = 0 forces the
-  // first generation, 2 / 3 the second / third for every n <= 8 (experiments).
+  // Two cells per thread with acc in registers and the shuffle/seam exchange (multi_reg3.cuh; multi_reg2.cuh) where it
+  // measured faster on B200 than the first generation below (profiles/r2_reg3_shapes.jsonl, cell-stage/s, third
+  // generation vs first): every n >= 5 (the first generation has only one cell per thread there), and for batches that
+  // fill the machine n = 4 (nz 200: 1.23e11 vs 1.09e11, nz 512: 1.57e11 vs 1.34e11), n = 3 (nz 100: 1.38e11 vs
+  // 1.37e11) and n = 1 (2.74e11 vs 2.53e11); n = 2 stays with the first generation (nz 100: 1.83e11 vs 1.87e11, nz
+  // 512: 2.47e11 vs 2.49e11), and so do batches too small to fill the machine (latency-bound: they want the most
+  // threads per column, 1 cell per thread).  CHROM_REG2 = 0 forces the first generation, 2 / 3 the second / third for
+  // every n <= 8 (experiments, A/B tests).
   {
     const int gen = reg_generation();
-    const bool second = getenv("CHROM_REG2") ? gen != 0 : n >= kReg2MinSpecies;
+    const bool fills_machine = (uint64_t)b.n_cols >= (uint64_t)sm_count * 2u;
+    const bool second = getenv("CHROM_REG2") ? gen != 0 : (n >= kReg2MinSpecies || (fills_machine && n != 2));
     if (second && multi_reg2_choose(b, sm_count, g)) return true;
   }
   const char* force = getenv("CHROM_REG_M");

@@ -32,6 +32,12 @@
 //       3  protocol 1 with branch-free seam code: the store and the arrival are predicated on lane 31, and on the
 //          consumer side EVERY lane waits on the barrier and loads the row (a broadcast), lane 0 keeps it by select;
 //          a stage then has no divergent branch at all.
+//       4  protocol 3 with a SPLIT step barrier: instead of `__syncthreads` at the top of a step every warp ARRIVES on
+//          a CTA-wide mbarrier there (count = warps) and WAITS for that phase only just before the step's last post
+//          (3.5 stages later, when the others have long arrived).  The ring stays safe - slot 0 of the next step is
+//          rewritten after everyone has finished the previous step, slots 1..3 were covered by the previous step's
+//          wait - but no warp stands still at the top of a step; warp 0 publishes the inlet row for itself and the
+//          redo flag is polled every 64 steps as in protocol 2.
 //     The mbarriers are initialised ONCE per kernel.  (Re-initialising them per run with mbarrier.inval +
 //     mbarrier.init stalled on B200: C5 and an abandoned Euler run never finished, first GPU session of this
 //     kernel.)  Instead the phase bookkeeping runs on a CTA-wide step counter that continues across runs and
@@ -111,7 +117,9 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
   __shared__ double colc[2];              // 2 max_i K_i, min_i (1 + fe lambda_i) of the current column
   __shared__ unsigned flags[32];          // SYNC 0: per warp, stage inputs posted so far in this run
   __shared__ unsigned long long badkey;   // min over threads of (first bad step << 1) | (NaN ? 0 : 1); ~0 = clean
-  __shared__ __align__(8) unsigned long long bars[(SYNC == 0) ? 1 : ((SYNC == 2) ? 2 : 1) * 8 * kMaxW];
+  __shared__ __align__(8) unsigned long long bars[(SYNC == 0) ? 1 : ((SYNC == 2) ? 2 : 1) * 8 * kMaxW + 1];
+  constexpr bool FLAT = (SYNC == 3 || SYNC == 4);    // predicated seam code
+  constexpr bool LOOSE = (SYNC == 2 || SYNC == 4);   // no __syncthreads at the top of a step
   extern __shared__ __align__(16) double seam3[];  // [8 slots][W warps][XS]: the last cell of each warp, per stage
                                                   // input; then cold[W][3 N + N N]: dense-fallback scratch per warp
 
@@ -127,9 +135,11 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
   uint32_t gbase = 0u;  // even; global step number at which the next run starts (seam phase bookkeeping)
   auto full_bar = [&](int slot, int w) { return &bars[slot * kMaxW + w]; };
   auto empty_bar = [&](int slot, int w) { return &bars[(8 + slot) * kMaxW + w]; };
+  unsigned long long* const step_bar = &bars[8 * kMaxW];  // SYNC 4 (never the same protocol as empty_bar)
   if (SYNC != 0) {
     const int nb = ((SYNC == 2) ? 16 : 8) * kMaxW;
     for (int i = tid; i < nb; i += (int)blockDim.x) mbar_init(&bars[i], 1u);
+    if (SYNC == 4 && tid == 0) mbar_init(&bars[8 * kMaxW], (unsigned)W);  // the split step barrier: one arrival per warp
     __syncthreads();
     // every ring slot starts out empty: one arrival completes phase 0 of its empty barrier, so that the producer of
     // use k always waits for phase k (parity k & 1) and the consumer of use k completes phase k + 1
@@ -236,9 +246,10 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
       // The last cell of a stage's OUTPUT (= the input of stage `slot & 3` of global step g) goes to ring slot `slot`
       // for the downstream warp.  Use k = g >> 1 of a slot: the producer waits for phase k of the slot's empty
       // barrier, its arrival completes phase k of the full barrier, the consumer's completes phase k + 1 of the empty.
-      auto post = [&](const double (&last)[N], int slot, uint32_t g) {
+      auto post = [&](const double (&last)[N], int slot, uint32_t g, bool wait_step = false, uint32_t g_step = 0u) {
         if (SYNC == 0) ++posted;
-        if (SYNC == 3) {
+        if (FLAT) {
+          if (SYNC == 4 && wait_step) mbar_wait(step_bar, g_step & 1u);  // everyone has finished the previous step
           const bool poster = (lane == 31) && (warp + 1 < W);
           double* dst = seam + ((size_t)slot * W + warp) * XS;
           if (N % 2 == 0) {
@@ -320,9 +331,9 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
 #pragma unroll
         for (int j = M - 1; j >= 1; --j) {
           cell(j, u[j - 1]);
-          if (j == M - 1) post(u[M - 1], slot_next, g_next);
+          if (j == M - 1) post(u[M - 1], slot_next, g_next, last, g);
         }
-        if (SYNC == 3) {  // warp-uniform: every lane waits and loads the row (a broadcast), lane 0 keeps it
+        if (FLAT) {  // warp-uniform: every lane waits and loads the row (a broadcast), lane 0 keeps it
           const double* srcp = &inlet[spar][irow][0];
           if (warp != 0) {
             mbar_wait(full_bar(slot, warp - 1), (g >> 1) & 1u);
@@ -370,7 +381,7 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
           }
         }
         cell(0, up);
-        if (M == 1) post(u[0], slot_next, g_next);
+        if (M == 1) post(u[0], slot_next, g_next, last, g);
       };
 
       post(y[M - 1], 0, G0);  // input of stage 1 of step 0 (G0 is even: slot 0)
@@ -379,7 +390,7 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
       for (uint32_t step = 0; step < steps; ++step) {
         const uint32_t g = G0 + step;
         const int spar = (int)(g & 1u);
-        if (SYNC != 2) {
+        if (!LOOSE) {
           for (int i = tid; i < N * ST; i += (int)blockDim.x) {  // inlet values of this step: [stage row][species]
             const int s = i % N, r = i / N;
             inlet[spar][r][s] = tabs[s][(size_t)step * ST + r];
@@ -410,6 +421,7 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
               break;
             }
           }
+          if (SYNC == 4) mbar_arrive_if(lane == 0, step_bar);  // "this warp has finished step g - 1": phase g
         }
         const int s0 = spar * 4, s1 = (spar ^ 1) * 4;
         if (METHOD == CHROM_RK4) {
@@ -479,6 +491,8 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
         if (SYNC == 2 && lane == 0 && warp >= 1)
           for (uint32_t g2 = gend; g2 < G1; ++g2)
             for (int i = 0; i < kIn; ++i) mbar_arrive(empty_bar((int)(g2 & 1u) * 4 + i, warp - 1));
+        if (SYNC == 4)  // the split step barrier has one phase per global step: arrivals exist for every g < gend
+          for (uint32_t g2 = gend; g2 < G1; ++g2) mbar_arrive_if(lane == 0, step_bar);
         gbase = G1;
       }
       if (again) return true;
@@ -507,6 +521,7 @@ rkern_t pick_reg3_n(int method, int sync) {
       case 1: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 1> : k_multi_reg3<N, 2, CHROM_EULER, 1>;
       case 2: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 2> : k_multi_reg3<N, 2, CHROM_EULER, 2>;
       case 3: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 3> : k_multi_reg3<N, 2, CHROM_EULER, 3>;
+      case 4: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 4> : k_multi_reg3<N, 2, CHROM_EULER, 4>;
     }
   }
   return nullptr;
