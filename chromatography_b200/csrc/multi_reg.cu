@@ -117,7 +117,7 @@ constexpr int kReg2MinSpecies = 5;
 
 // Generation of the 2-cells-per-thread kernels (n <= 8): 3 = multi_reg3.cuh (guard per column run), 2 = multi_reg2.cuh.
 // CHROM_REG2 = 2 / 3 forces one (experiments, A/B tests), CHROM_REG3_SYNC picks the seam protocol of the third.
-constexpr int kReg3DefaultSync = 3;
+constexpr int kReg3DefaultSync = 4;
 static int reg_generation() {
   const char* v = getenv("CHROM_REG2");
   return v ? atoi(v) : 3;
@@ -125,7 +125,7 @@ static int reg_generation() {
 static int reg3_sync() {
   const char* v = getenv("CHROM_REG3_SYNC");
   const int s = v ? atoi(v) : kReg3DefaultSync;
-  return (s < 0 || s > 4) ? kReg3DefaultSync : s;
+  return (s < 0 || s > 5) ? kReg3DefaultSync : s;
 }
 
 static bool multi_reg2_choose(const BatchDev& b, int sm_count, LaunchGeom* g) {
@@ -163,7 +163,8 @@ static bool multi_reg2_choose(const BatchDev& b, int sm_count, LaunchGeom* g) {
            b.method == CHROM_RK4 ? "RK4" : "Euler",
            gen == 3 ? (sync == 0 ? ",seam=flags" : sync == 1 ? ",seam=mbarrier" : sync == 2 ? ",seam=mbarrier-nobar"
                                                                  : sync == 3 ? ",seam=mbarrier-flat"
-                                                                             : ",seam=mbarrier-flat-splitbar")
+                                                                 : sync == 4 ? ",seam=mbarrier-flat-splitbar"
+                                                                             : ",seam=mbarrier-flat-splitbar-prefetch")
                     : "", T, M,
            per_sm, g->grid.x);
   g->name = buf;

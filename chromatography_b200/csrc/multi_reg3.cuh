@@ -38,6 +38,9 @@
 //          rewritten after everyone has finished the previous step, slots 1..3 were covered by the previous step's
 //          wait - but no warp stands still at the top of a step; warp 0 publishes the inlet row for itself and the
 //          redo flag is polled every 64 steps as in protocol 2.
+//       5  protocol 4, and warp 0 requests the NEXT step's inlet row with cp.async at the top of a step (the row it is
+//          about to use was requested a step earlier): no global-load latency on the path of the warp that heads
+//          the column's dependence chain.
 //     The mbarriers are initialised ONCE per kernel.  (Re-initialising them per run with mbarrier.inval +
 //     mbarrier.init stalled on B200: C5 and an abandoned Euler run never finished, first GPU session of this
 //     kernel.)  Instead the phase bookkeeping runs on a CTA-wide step counter that continues across runs and
@@ -118,8 +121,10 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
   __shared__ unsigned flags[32];          // SYNC 0: per warp, stage inputs posted so far in this run
   __shared__ unsigned long long badkey;   // min over threads of (first bad step << 1) | (NaN ? 0 : 1); ~0 = clean
   __shared__ __align__(8) unsigned long long bars[(SYNC == 0) ? 1 : ((SYNC == 2) ? 2 : 1) * 8 * kMaxW + 1];
-  constexpr bool FLAT = (SYNC == 3 || SYNC == 4);    // predicated seam code
-  constexpr bool LOOSE = (SYNC == 2 || SYNC == 4);   // no __syncthreads at the top of a step
+  constexpr bool FLAT = (SYNC >= 3);                 // predicated seam code
+  constexpr bool LOOSE = (SYNC == 2 || SYNC >= 4);   // no __syncthreads at the top of a step
+  constexpr bool SPLIT = (SYNC >= 4);                // split step barrier: arrive at the top, wait before the last post
+  constexpr bool PREFETCH = (SYNC == 5);             // warp 0 fetches the NEXT step's inlet row with cp.async
   extern __shared__ __align__(16) double seam3[];  // [8 slots][W warps][XS]: the last cell of each warp, per stage
                                                   // input; then cold[W][3 N + N N]: dense-fallback scratch per warp
 
@@ -135,11 +140,11 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
   uint32_t gbase = 0u;  // even; global step number at which the next run starts (seam phase bookkeeping)
   auto full_bar = [&](int slot, int w) { return &bars[slot * kMaxW + w]; };
   auto empty_bar = [&](int slot, int w) { return &bars[(8 + slot) * kMaxW + w]; };
-  unsigned long long* const step_bar = &bars[8 * kMaxW];  // SYNC 4 (never the same protocol as empty_bar)
+  unsigned long long* const step_bar = &bars[8 * kMaxW];  // SPLIT (never the same protocol as empty_bar)
   if (SYNC != 0) {
     const int nb = ((SYNC == 2) ? 16 : 8) * kMaxW;
     for (int i = tid; i < nb; i += (int)blockDim.x) mbar_init(&bars[i], 1u);
-    if (SYNC == 4 && tid == 0) mbar_init(&bars[8 * kMaxW], (unsigned)W);  // the split step barrier: one arrival per warp
+    if (SPLIT && tid == 0) mbar_init(&bars[8 * kMaxW], (unsigned)W);  // the split step barrier: one arrival per warp
     __syncthreads();
     // every ring slot starts out empty: one arrival completes phase 0 of its empty barrier, so that the producer of
     // use k always waits for phase k (parity k & 1) and the consumer of use k completes phase k + 1
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
       auto post = [&](const double (&last)[N], int slot, uint32_t g, bool wait_step = false, uint32_t g_step = 0u) {
         if (SYNC == 0) ++posted;
         if (FLAT) {
-          if (SYNC == 4 && wait_step) mbar_wait(step_bar, g_step & 1u);  // everyone has finished the previous step
+          if (SPLIT && wait_step) mbar_wait(step_bar, g_step & 1u);  // everyone has finished the previous step
           const bool poster = (lane == 31) && (warp + 1 < W);
           double* dst = seam + ((size_t)slot * W + warp) * XS;
           if (N % 2 == 0) {
@@ -384,6 +389,20 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
         if (M == 1) post(u[0], slot_next, g_next, last, g);
       };
 
+      // warp 0, PREFETCH: asynchronous copy of one step's inlet row [stage row][species] into buffer `par`
+      auto inlet_fetch = [&](uint32_t step, int par) {
+        for (int i = lane; i < N * ST; i += 32) {
+          const int s = i % N, r = i / N;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&inlet[par][r][s])),
+                       "l"(tabs[s] + (size_t)step * ST + r)
+                       : "memory");
+        }
+      };
+      if (PREFETCH && warp == 0 && steps > 0u) {
+        asm volatile("cp.async.wait_all;" ::: "memory");  // a request of an abandoned run may still be in flight
+        __syncwarp();
+        inlet_fetch(0u, (int)(G0 & 1u));
+      }
       post(y[M - 1], 0, G0);  // input of stage 1 of step 0 (G0 is even: slot 0)
       bool abandon = false;
       uint32_t done = steps;  // steps whose stage inputs were all posted and consumed when the run ended
@@ -408,11 +427,19 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
           }
         } else {
           if (warp == 0) {  // only warp 0 reads the inlet: it publishes the row for itself
-            for (int i = lane; i < N * ST; i += 32) {
-              const int s = i % N, r = i / N;
-              inlet[spar][r][s] = tabs[s][(size_t)step * ST + r];
+            if (PREFETCH) {
+              // this step's row was requested one step ago (before the loop for step 0); request the next one now, so
+              // that the load latency never sits on warp 0's path (warp 0 heads the dependence chain of the column)
+              asm volatile("cp.async.wait_all;" ::: "memory");
+              __syncwarp();
+              if (step + 1u < steps) inlet_fetch(step + 1u, spar ^ 1);
+            } else {
+              for (int i = lane; i < N * ST; i += 32) {
+                const int s = i % N, r = i / N;
+                inlet[spar][r][s] = tabs[s][(size_t)step * ST + r];
+              }
+              __syncwarp();
             }
-            __syncwarp();
           }
           if (!GUARD && (step % kReg3CheckEvery) == kReg3CheckEvery - 1) {
             if (__syncthreads_or(sus ? 1 : 0)) {
@@ -421,7 +448,7 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
               break;
             }
           }
-          if (SYNC == 4) mbar_arrive_if(lane == 0, step_bar);  // "this warp has finished step g - 1": phase g
+          if (SPLIT) mbar_arrive_if(lane == 0, step_bar);  // "this warp has finished step g - 1": phase g
         }
         const int s0 = spar * 4, s1 = (spar ^ 1) * 4;
         if (METHOD == CHROM_RK4) {
@@ -491,7 +518,7 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
         if (SYNC == 2 && lane == 0 && warp >= 1)
           for (uint32_t g2 = gend; g2 < G1; ++g2)
             for (int i = 0; i < kIn; ++i) mbar_arrive(empty_bar((int)(g2 & 1u) * 4 + i, warp - 1));
-        if (SYNC == 4)  // the split step barrier has one phase per global step: arrivals exist for every g < gend
+        if (SPLIT)  // the split step barrier has one phase per global step: arrivals exist for every g < gend
           for (uint32_t g2 = gend; g2 < G1; ++g2) mbar_arrive_if(lane == 0, step_bar);
         gbase = G1;
       }
@@ -522,6 +549,7 @@ rkern_t pick_reg3_n(int method, int sync) {
       case 2: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 2> : k_multi_reg3<N, 2, CHROM_EULER, 2>;
       case 3: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 3> : k_multi_reg3<N, 2, CHROM_EULER, 3>;
       case 4: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 4> : k_multi_reg3<N, 2, CHROM_EULER, 4>;
+      case 5: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 5> : k_multi_reg3<N, 2, CHROM_EULER, 5>;
     }
   }
   return nullptr;
