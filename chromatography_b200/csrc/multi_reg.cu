@@ -125,7 +125,7 @@ static int reg_generation() {
 static int reg3_sync() {
   const char* v = getenv("CHROM_REG3_SYNC");
   const int s = v ? atoi(v) : kReg3DefaultSync;
-  return (s < 0 || s > 5) ? kReg3DefaultSync : s;
+  return (s == 0 || s == 3 || s == 4) ? s : kReg3DefaultSync;  // the protocols multi_reg3.cuh builds
 }
 
 static bool multi_reg2_choose(const BatchDev& b, int sm_count, LaunchGeom* g) {
@@ -161,11 +161,7 @@ static bool multi_reg2_choose(const BatchDev& b, int sm_count, LaunchGeom* g) {
   snprintf(buf, sizeof buf,
            "multi_reg%d<n=%d,%s,fast-scan-LU%s> threads/col=%d cells/thread=%d CTAs/SM=%d persistent grid=%u", gen, n,
            b.method == CHROM_RK4 ? "RK4" : "Euler",
-           gen == 3 ? (sync == 0 ? ",seam=flags" : sync == 1 ? ",seam=mbarrier" : sync == 2 ? ",seam=mbarrier-nobar"
-                                                                 : sync == 3 ? ",seam=mbarrier-flat"
-                                                                 : sync == 4 ? ",seam=mbarrier-flat-splitbar"
-                                                                             : ",seam=mbarrier-flat-splitbar-prefetch")
-                    : "", T, M,
+           gen == 3 ? (sync == 0 ? ",seam=flags" : sync == 3 ? ",seam=mbarrier" : ",seam=mbarrier+split-step-barrier") : "", T, M,
            per_sm, g->grid.x);
   g->name = buf;
   return true;

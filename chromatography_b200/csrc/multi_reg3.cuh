@@ -18,34 +18,28 @@
 //     pass the bound takes exactly the arithmetic it took before, so results are bit-identical to k_multi_reg2;
 //     a column that fails it is computed by the guarded code alone, also bit-identical to k_multi_reg2.
 //
-//  2. SYNC selects the warp-seam protocol:
-//       0  st.release / ld.acquire counters + one CTA barrier per step (multi_reg2.cuh's protocol; the release store
-//          compiles to MEMBAR.ALL.CTA + STS);
-//       1  one mbarrier per (ring slot, seam): the producer's lane 31 stores the row (STS.128) and arrives
-//          (SYNCS.ARRIVE, release semantics, no MEMBAR), the consumer's lane 0 waits with mbarrier.try_wait (the
-//          warp sleeps in hardware instead of polling through the LSU); the CTA barrier per step stays and bounds
-//          the skew, so the 8-slot ring needs no back-pressure;
-//       2  full AND empty mbarriers, no CTA barrier in the step loop: a warp waits for its upstream warp's value and
-//          for its downstream warp to have consumed the slot it is about to overwrite (two steps back), nothing
-//          else; warp 0 publishes the inlet row for itself; the redo flag is polled with a CTA barrier every 64
-//          steps only.
-//       3  protocol 1 with branch-free seam code: the store and the arrival are predicated on lane 31, and on the
-//          consumer side EVERY lane waits on the barrier and loads the row (a broadcast), lane 0 keeps it by select;
-//          a stage then has no divergent branch at all.
-//       4  protocol 3 with a SPLIT step barrier: instead of `__syncthreads` at the top of a step every warp ARRIVES on
-//          a CTA-wide mbarrier there (count = warps) and WAITS for that phase only just before the step's last post
-//          (3.5 stages later, when the others have long arrived).  The ring stays safe - slot 0 of the next step is
-//          rewritten after everyone has finished the previous step, slots 1..3 were covered by the previous step's
-//          wait - but no warp stands still at the top of a step; warp 0 publishes the inlet row for itself and the
-//          redo flag is polled every 64 steps as in protocol 2.
-//       5  protocol 4, and warp 0 requests the NEXT step's inlet row with cp.async at the top of a step (the row it is
-//          about to use was requested a step earlier): no global-load latency on the path of the warp that heads
-//          the column's dependence chain.
+//  2. SYNC selects the warp-seam protocol.  Six were measured on C5 (profiles/r2_c5_experiments.txt); three are built:
+//       0  st.release / ld.acquire counters + one CTA barrier per step: multi_reg2.cuh's protocol, kept as the A/B
+//          baseline (the release store compiles to MEMBAR.ALL.CTA + STS, the wait is a polling loop).  438 ms.
+//       3  one mbarrier per (ring slot, seam): the producer's lane 31 stores the row (STS.128) and arrives
+//          (SYNCS.ARRIVE: release semantics, no MEMBAR), the consumer waits with mbarrier.try_wait (the warp sleeps
+//          in hardware instead of polling through the LSU).  Store and arrival are PREDICATED on lane 31 rather than
+//          inside a divergent branch, and on the consumer side every lane waits and the row load is predicated on
+//          lane 0, so a stage has no divergent branch at all.  The CTA barrier per step stays and bounds the skew
+//          (the 8-slot ring needs no back-pressure).  392 ms (the same with the seam code in branches: 408 ms).
+//       4  protocol 3 with a SPLIT step barrier (the default): instead of `__syncthreads` at the top of a step every
+//          warp ARRIVES on a CTA-wide mbarrier there (count = warps) and WAITS for that phase only just before the
+//          step's last post (3.5 stages later, when the others have long arrived).  The ring stays safe - slot 0 of
+//          the next step is rewritten after everyone has finished the previous step, slots 1..3 were covered by the
+//          previous step's wait - but no warp stands still at the top of a step; warp 0 publishes the inlet row for
+//          itself and the redo flag is polled with a CTA barrier every 64 steps.  372 ms.
+//     Measured and removed: full AND empty mbarriers with no step barrier at all (a warp runs ahead until the ring
+//     is full: 517 ms - slack has to be bounded), and protocol 4 with the next inlet row requested by cp.async (382 ms).
 //     The mbarriers are initialised ONCE per kernel.  (Re-initialising them per run with mbarrier.inval +
 //     mbarrier.init stalled on B200: C5 and an abandoned Euler run never finished, first GPU session of this
 //     kernel.)  Instead the phase bookkeeping runs on a CTA-wide step counter that continues across runs and
 //     columns: input i of global step g lives in ring slot (g & 1) * 4 + i and is use g >> 1 of that slot's
-//     barriers, and a run ends by topping every barrier up to the same number of completed phases (`settle`).
+//     barrier, and a run ends by topping every barrier up to the same number of completed phases (`settle`).
 #pragma once
 #include <type_traits>
 
@@ -73,7 +67,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       : "memory");
 }
 
-// predicated forms (SYNC 3): the seam store and the arrival are issued by every lane under a predicate instead of
+// predicated forms (SYNC 3, 4): the seam store and the arrival are issued by every lane under a predicate instead of
 // inside a divergent branch (no BSSY / BRA / BSYNC around five instructions)
 __device__ __forceinline__ void st_shared_v2_if(bool p, double* dst, double a, double b) {
   asm volatile(
@@ -106,7 +100,7 @@ __device__ __forceinline__ void mbar_arrive_if(bool p, unsigned long long* bar) 
       : "memory");
 }
 
-constexpr int kReg3CheckEvery = 64;  // SYNC 2: steps between two CTA-wide polls of the redo flag
+constexpr int kReg3CheckEvery = 64;  // SYNC 4: steps between two CTA-wide polls of the redo flag
 
 template <int N, int M, int METHOD, int SYNC>
 __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const BatchDev b) {
@@ -120,11 +114,10 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
   __shared__ double colc[2];              // 2 max_i K_i, min_i (1 + fe lambda_i) of the current column
   __shared__ unsigned flags[32];          // SYNC 0: per warp, stage inputs posted so far in this run
   __shared__ unsigned long long badkey;   // min over threads of (first bad step << 1) | (NaN ? 0 : 1); ~0 = clean
-  __shared__ __align__(8) unsigned long long bars[(SYNC == 0) ? 1 : ((SYNC == 2) ? 2 : 1) * 8 * kMaxW + 1];
-  constexpr bool FLAT = (SYNC >= 3);                 // predicated seam code
-  constexpr bool LOOSE = (SYNC == 2 || SYNC >= 4);   // no __syncthreads at the top of a step
-  constexpr bool SPLIT = (SYNC >= 4);                // split step barrier: arrive at the top, wait before the last post
-  constexpr bool PREFETCH = (SYNC == 5);             // warp 0 fetches the NEXT step's inlet row with cp.async
+  __shared__ __align__(8) unsigned long long bars[(SYNC == 0) ? 1 : 8 * kMaxW + 1];  // [slot][seam], then the step barrier
+  static_assert(SYNC == 0 || SYNC == 3 || SYNC == 4, "seam protocols built: 0, 3, 4");
+  constexpr bool FLAT = (SYNC >= 3);   // mbarrier seam, predicated seam code
+  constexpr bool SPLIT = (SYNC == 4);  // split step barrier: arrive at the top of a step, wait before its last post
   extern __shared__ __align__(16) double seam3[];  // [8 slots][W warps][XS]: the last cell of each warp, per stage
                                                   // input; then cold[W][3 N + N N]: dense-fallback scratch per warp
 
@@ -139,17 +132,10 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
   const uint32_t steps = b.steps;
   uint32_t gbase = 0u;  // even; global step number at which the next run starts (seam phase bookkeeping)
   auto full_bar = [&](int slot, int w) { return &bars[slot * kMaxW + w]; };
-  auto empty_bar = [&](int slot, int w) { return &bars[(8 + slot) * kMaxW + w]; };
-  unsigned long long* const step_bar = &bars[8 * kMaxW];  // SPLIT (never the same protocol as empty_bar)
-  if (SYNC != 0) {
-    const int nb = ((SYNC == 2) ? 16 : 8) * kMaxW;
-    for (int i = tid; i < nb; i += (int)blockDim.x) mbar_init(&bars[i], 1u);
-    if (SPLIT && tid == 0) mbar_init(&bars[8 * kMaxW], (unsigned)W);  // the split step barrier: one arrival per warp
-    __syncthreads();
-    // every ring slot starts out empty: one arrival completes phase 0 of its empty barrier, so that the producer of
-    // use k always waits for phase k (parity k & 1) and the consumer of use k completes phase k + 1
-    if (SYNC == 2)
-      for (int i = tid; i < 8 * kMaxW; i += (int)blockDim.x) mbar_arrive(&bars[8 * kMaxW + i]);
+  unsigned long long* const step_bar = &bars[(SYNC == 0) ? 0 : 8 * kMaxW];  // SPLIT only
+  if (FLAT) {
+    for (int i = tid; i < 8 * kMaxW; i += (int)blockDim.x) mbar_init(&bars[i], 1u);
+    if (SPLIT && tid == 0) mbar_init(step_bar, (unsigned)W);  // one arrival per warp and step
     __syncthreads();
   }
 
@@ -204,7 +190,7 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
     auto run = [&](auto guard_tag) -> bool {
       constexpr bool GUARD = decltype(guard_tag)::value;
       __syncthreads();  // nobody is still inside the previous run's seam protocol / reading badkey
-      if (SYNC == 0 && tid < 32) flags[tid] = 0u;
+      if (!FLAT && tid < 32) flags[tid] = 0u;
       const uint32_t G0 = gbase;  // this run's step t is global step G0 + t
       if (tid == 0) badkey = ~0ull;
       double y[M][N], u[M][N], acc[M][N];
@@ -249,10 +235,9 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
       bool sus = false;  // GUARD = false: some cell of this thread failed the sufficient bound (sticky)
 
       // The last cell of a stage's OUTPUT (= the input of stage `slot & 3` of global step g) goes to ring slot `slot`
-      // for the downstream warp.  Use k = g >> 1 of a slot: the producer waits for phase k of the slot's empty
-      // barrier, its arrival completes phase k of the full barrier, the consumer's completes phase k + 1 of the empty.
+      // for the downstream warp; its arrival completes phase g >> 1 of the slot's barrier (SYNC 0: the warp's counter
+      // of posted inputs moves on).  wait_step: this is the step's last post (SPLIT waits for the step barrier first).
       auto post = [&](const double (&last)[N], int slot, uint32_t g, bool wait_step = false, uint32_t g_step = 0u) {
-        if (SYNC == 0) ++posted;
         if (FLAT) {
           if (SPLIT && wait_step) mbar_wait(step_bar, g_step & 1u);  // everyone has finished the previous step
           const bool poster = (lane == 31) && (warp + 1 < W);
@@ -265,22 +250,14 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
             for (int s = 0; s < N; ++s) st_shared_if(poster, dst + s, last[s]);
           }
           mbar_arrive_if(poster, full_bar(slot, warp));
-          return;
-        }
-        if (lane == 31 && warp + 1 < W) {
-          double* dst = seam + ((size_t)slot * W + warp) * XS;
-          if (SYNC == 2) mbar_wait(empty_bar(slot, warp), (g >> 1) & 1u);
-          if (SYNC != 0 && N % 2 == 0) {  // 16-byte rows: STS.128
-#pragma unroll
-            for (int s = 0; s + 1 < N; s += 2) reinterpret_cast<double2*>(dst)[s / 2] = make_double2(last[s], last[s + 1]);
-          } else {
+        } else {
+          ++posted;
+          if (lane == 31 && warp + 1 < W) {
+            double* dst = seam + ((size_t)slot * W + warp) * XS;
 #pragma unroll
             for (int s = 0; s < N; ++s) dst[s] = last[s];
-          }
-          if (SYNC == 0)
             st_release_cta(&flags[warp], posted);
-          else
-            mbar_arrive(full_bar(slot, warp));
+          }
         }
       };
 
@@ -363,53 +340,25 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
 #pragma unroll
             for (int s = 0; s < N; ++s) up[s] = inlet[spar][irow][s];
           } else {
-            if (SYNC == 0) {
-              const unsigned need = posted - (M > 1 ? 1u : 0u);  // inputs this warp had posted when the stage began
-              while ((int)(ld_acquire_cta(&flags[warp - 1]) - need) < 0) {
-              }
-            } else {
-              mbar_wait(full_bar(slot, warp - 1), (g >> 1) & 1u);
+            const unsigned need = posted - (M > 1 ? 1u : 0u);  // inputs this warp had posted when the stage began
+            while ((int)(ld_acquire_cta(&flags[warp - 1]) - need) < 0) {
             }
             const double* srcp = seam + ((size_t)slot * W + (warp - 1)) * XS;
-            if (SYNC != 0 && N % 2 == 0) {
 #pragma unroll
-              for (int s = 0; s + 1 < N; s += 2) {
-                const double2 t = reinterpret_cast<const double2*>(srcp)[s / 2];
-                up[s] = t.x;
-                up[s + 1] = t.y;
-              }
-            } else {
-#pragma unroll
-              for (int s = 0; s < N; ++s) up[s] = srcp[s];
-            }
-            if (SYNC == 2) mbar_arrive(empty_bar(slot, warp - 1));  // release: the reads above are done
+            for (int s = 0; s < N; ++s) up[s] = srcp[s];
           }
         }
         cell(0, up);
         if (M == 1) post(u[0], slot_next, g_next, last, g);
       };
 
-      // warp 0, PREFETCH: asynchronous copy of one step's inlet row [stage row][species] into buffer `par`
-      auto inlet_fetch = [&](uint32_t step, int par) {
-        for (int i = lane; i < N * ST; i += 32) {
-          const int s = i % N, r = i / N;
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(&inlet[par][r][s])),
-                       "l"(tabs[s] + (size_t)step * ST + r)
-                       : "memory");
-        }
-      };
-      if (PREFETCH && warp == 0 && steps > 0u) {
-        asm volatile("cp.async.wait_all;" ::: "memory");  // a request of an abandoned run may still be in flight
-        __syncwarp();
-        inlet_fetch(0u, (int)(G0 & 1u));
-      }
       post(y[M - 1], 0, G0);  // input of stage 1 of step 0 (G0 is even: slot 0)
       bool abandon = false;
       uint32_t done = steps;  // steps whose stage inputs were all posted and consumed when the run ended
       for (uint32_t step = 0; step < steps; ++step) {
         const uint32_t g = G0 + step;
         const int spar = (int)(g & 1u);
-        if (!LOOSE) {
+        if (!SPLIT) {
           for (int i = tid; i < N * ST; i += (int)blockDim.x) {  // inlet values of this step: [stage row][species]
             const int s = i % N, r = i / N;
             inlet[spar][r][s] = tabs[s][(size_t)step * ST + r];
@@ -427,19 +376,11 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
           }
         } else {
           if (warp == 0) {  // only warp 0 reads the inlet: it publishes the row for itself
-            if (PREFETCH) {
-              // this step's row was requested one step ago (before the loop for step 0); request the next one now, so
-              // that the load latency never sits on warp 0's path (warp 0 heads the dependence chain of the column)
-              asm volatile("cp.async.wait_all;" ::: "memory");
-              __syncwarp();
-              if (step + 1u < steps) inlet_fetch(step + 1u, spar ^ 1);
-            } else {
-              for (int i = lane; i < N * ST; i += 32) {
-                const int s = i % N, r = i / N;
-                inlet[spar][r][s] = tabs[s][(size_t)step * ST + r];
-              }
-              __syncwarp();
+            for (int i = lane; i < N * ST; i += 32) {
+              const int s = i % N, r = i / N;
+              inlet[spar][r][s] = tabs[s][(size_t)step * ST + r];
             }
+            __syncwarp();
           }
           if (!GUARD && (step % kReg3CheckEvery) == kReg3CheckEvery - 1) {
             if (__syncthreads_or(sus ? 1 : 0)) {
@@ -448,7 +389,7 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
               break;
             }
           }
-          if (SPLIT) mbar_arrive_if(lane == 0, step_bar);  // "this warp has finished step g - 1": phase g
+          mbar_arrive_if(lane == 0, step_bar);  // "this warp has finished step g - 1": one of the W arrivals of phase g
         }
         const int s0 = spar * 4, s1 = (spar ^ 1) * 4;
         if (METHOD == CHROM_RK4) {
@@ -506,19 +447,16 @@ __global__ void __launch_bounds__(reg2_max_threads(N, M), 1) k_multi_reg3(const 
         else
           __syncthreads();
       }
-      if (SYNC != 0) {
+      if (FLAT) {
         // settle: nobody waits on a seam barrier any more (CTA barrier above).  Posted so far: input 0 of every global
-        // step <= gend, inputs 1..3 of every step < gend; consumed: every input of every step < gend.  Top each
-        // barrier up to the phases of all steps < G1 (the next even step number > gend), where the next run starts.
+        // step <= gend, inputs 1..3 of every step < gend.  Top each barrier up to the phases of all steps < G1 (the
+        // next even step number > gend), where the next run starts.
         const uint32_t gend = G0 + done, G1 = (gend + 2u) & ~1u;
         constexpr int kIn = (METHOD == CHROM_RK4) ? 4 : 1;  // stage inputs per step that cross a seam
         if (lane == 31 && warp + 1 < W)
           for (uint32_t g2 = gend; g2 < G1; ++g2)
             for (int i = (g2 == gend ? 1 : 0); i < kIn; ++i) mbar_arrive(full_bar((int)(g2 & 1u) * 4 + i, warp));
-        if (SYNC == 2 && lane == 0 && warp >= 1)
-          for (uint32_t g2 = gend; g2 < G1; ++g2)
-            for (int i = 0; i < kIn; ++i) mbar_arrive(empty_bar((int)(g2 & 1u) * 4 + i, warp - 1));
-        if (SPLIT)  // the split step barrier has one phase per global step: arrivals exist for every g < gend
+        if (SPLIT)  // the step barrier has one phase per global step: arrivals exist for every g < gend
           for (uint32_t g2 = gend; g2 < G1; ++g2) mbar_arrive_if(lane == 0, step_bar);
         gbase = G1;
       }
@@ -545,11 +483,8 @@ rkern_t pick_reg3_n(int method, int sync) {
     const bool rk4 = method == CHROM_RK4;
     switch (sync) {
       case 0: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 0> : k_multi_reg3<N, 2, CHROM_EULER, 0>;
-      case 1: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 1> : k_multi_reg3<N, 2, CHROM_EULER, 1>;
-      case 2: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 2> : k_multi_reg3<N, 2, CHROM_EULER, 2>;
       case 3: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 3> : k_multi_reg3<N, 2, CHROM_EULER, 3>;
       case 4: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 4> : k_multi_reg3<N, 2, CHROM_EULER, 4>;
-      case 5: return rk4 ? k_multi_reg3<N, 2, CHROM_RK4, 5> : k_multi_reg3<N, 2, CHROM_EULER, 5>;
     }
   }
   return nullptr;

@@ -44,10 +44,8 @@ MULTI_CASES = [
     (6, 200, cb.ARITH_FAST, {}),                       # k_multi_reg3, ragged last warp
     (5, 97, cb.ARITH_FAST, {}),                        # k_multi_reg3, odd n, nz not a multiple of anything
     (8, 512, cb.ARITH_FAST, {"CHROM_REG3_SYNC": "0"}),  # k_multi_reg3, release/acquire counters instead of mbarriers
-    (8, 512, cb.ARITH_FAST, {"CHROM_REG3_SYNC": "2"}),  # k_multi_reg3, full + empty mbarriers, no per-step CTA barrier
-    (7, 300, cb.ARITH_FAST, {"CHROM_REG3_SYNC": "1"}),  # k_multi_reg3, mbarrier seam inside divergent branches
     (8, 512, cb.ARITH_FAST, {"CHROM_REG3_SYNC": "3"}),  # k_multi_reg3, predicated seam code, CTA barrier per step
-    (6, 200, cb.ARITH_FAST, {"CHROM_REG3_SYNC": "5"}),  # k_multi_reg3, split step barrier + cp.async inlet prefetch
+    (3, 300, cb.ARITH_FAST, {}),                        # k_multi_reg3 at n = 3 (machine-filling batch: 600 columns)
     (8, 512, cb.ARITH_FAST, {"CHROM_REG2": "2"}),      # k_multi_reg2 (second generation, guard per cell)
     (2, 300, cb.ARITH_FAST, {}),                       # k_multi_reg: shared-memory exchange, one barrier per stage
     (12, 256, cb.ARITH_FAST, {}),                      # k_multi_reg, acc in shared slots
