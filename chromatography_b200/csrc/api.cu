@@ -919,7 +919,17 @@ static int32_t solve_pipelined(chrom_cuda_ctx* ctx, chrom_cuda_plan* plan, doubl
   if (!worth) return 1;
   const double t0 = now_ms();
   uint64_t launches = 0, bytes = 0;
-  std::vector<std::vector<cudaEvent_t>> events(plan->shards.size());
+  // events of the chunks and slices, per shard: destroyed on EVERY exit path (CUDA_TRY returns from inside the loops;
+  // the plan's destructor, which solve_common runs next, drains the streams the events were recorded on)
+  struct EventBag {
+    std::vector<std::vector<cudaEvent_t>> per_shard;
+    explicit EventBag(size_t n) : per_shard(n) {}
+    ~EventBag() {
+      for (auto& v : per_shard)
+        for (cudaEvent_t e : v) cudaEventDestroy(e);
+    }
+  } bag(plan->shards.size());
+  std::vector<std::vector<cudaEvent_t>>& events = bag.per_shard;
   int32_t rc = CHROM_OK;
   // round-robin over shards so every device has work queued before any host-side wait
   std::vector<uint64_t> next(plan->shards.size(), 0);
@@ -1034,6 +1044,7 @@ static int32_t solve_pipelined(chrom_cuda_ctx* ctx, chrom_cuda_plan* plan, doubl
     if (e == cudaSuccess) cudaEventElapsedTime(&sh.kernel_ms, d.ev[2], d.ev[3]);
     kmax = std::max(kmax, sh.kernel_ms);
     for (cudaEvent_t ev : events[si]) cudaEventDestroy(ev);
+    events[si].clear();
     if (e != cudaSuccess && rc == CHROM_OK)
       rc = fail(ctx, CHROM_ERR_CUDA, format("pipelined solve failed: %s", cudaGetErrorString(e)));
   }
