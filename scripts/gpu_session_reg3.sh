@@ -1,4 +1,6 @@
 #!/bin/bash
+# (Provenance of profiles/r2_reg3_sessions.txt.  Seam protocols 1, 2, 5 and 6 named here were measured and then removed from
+# the build: CHROM_REG3_SYNC now accepts 0, 3 and 4; see csrc/multi_reg3.cuh and profiles/r2_c5_experiments.txt.)
 # One gpurun call: parity of k_multi_reg3 against k_multi_reg2, C5 timing of every seam protocol, ncu captures of the
 # two mbarrier variants, then the whole GPU suite and the default bench line.
 mkdir -p gpurun_out

@@ -1,4 +1,6 @@
 #!/bin/bash
+# (Provenance of profiles/r2_reg3_sessions.txt.  Seam protocols 1, 2, 5 and 6 named here were measured and then removed from
+# the build: CHROM_REG3_SYNC now accepts 0, 3 and 4; see csrc/multi_reg3.cuh and profiles/r2_c5_experiments.txt.)
 # Second reg3 session: every step under its own timeout.  C5 timing of the RK4 variants, then probes that locate the
 # Euler stall seen in the first session (which kernel generation / seam protocol / kind of column).
 mkdir -p gpurun_out

@@ -1,4 +1,6 @@
 #!/bin/bash
+# (Provenance of profiles/r2_reg3_sessions.txt.  Seam protocols 1, 2, 5 and 6 named here were measured and then removed from
+# the build: CHROM_REG3_SYNC now accepts 0, 3 and 4; see csrc/multi_reg3.cuh and profiles/r2_c5_experiments.txt.)
 # Third reg3 session (mbarriers initialised once, phase bookkeeping across runs): probes of the shapes that stalled,
 # C5 timing of the mbarrier variants, the whole GPU suite, the default bench line, one full ncu capture.
 mkdir -p gpurun_out

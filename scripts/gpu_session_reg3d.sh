@@ -1,4 +1,6 @@
 #!/bin/bash
+# (Provenance of profiles/r2_reg3_sessions.txt.  Seam protocols 1, 2, 5 and 6 named here were measured and then removed from
+# the build: CHROM_REG3_SYNC now accepts 0, 3 and 4; see csrc/multi_reg3.cuh and profiles/r2_c5_experiments.txt.)
 # Fourth reg3 session: parity of every seam protocol (incl. 3 = predicated seam code), C5 timing of protocols 1 and 3,
 # then - with the faster of the two selected through CHROM_REG3_SYNC - the whole GPU suite, the default bench line and
 # one full ncu capture of the C5 kernel.

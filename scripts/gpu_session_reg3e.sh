@@ -1,4 +1,6 @@
 #!/bin/bash
+# (Provenance of profiles/r2_reg3_sessions.txt.  Seam protocols 1, 2, 5 and 6 named here were measured and then removed from
+# the build: CHROM_REG3_SYNC now accepts 0, 3 and 4; see csrc/multi_reg3.cuh and profiles/r2_c5_experiments.txt.)
 # Fifth reg3 session: the split step barrier (CHROM_REG3_SYNC=4) against the default (3) on C5, parity of every protocol.
 mkdir -p gpurun_out
 timeout 400 python -m pytest tests/test_gpu_multi_reg3.py -q --timeout 100 --timeout-method thread > gpurun_out/reg3_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/reg3_tests.log

@@ -1,4 +1,6 @@
 #!/bin/bash
+# (Provenance of profiles/r2_reg3_sessions.txt.  Seam protocols 1, 2, 5 and 6 named here were measured and then removed from
+# the build: CHROM_REG3_SYNC now accepts 0, 3 and 4; see csrc/multi_reg3.cuh and profiles/r2_c5_experiments.txt.)
 # Sixth reg3 session: early barrier tests + late last post (CHROM_REG3_SYNC=6) against the default (4) on C5.
 mkdir -p gpurun_out
 timeout 150 python -m pytest tests/test_gpu_multi_reg3.py -q --timeout 60 --timeout-method thread > gpurun_out/reg3_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/reg3_tests.log
